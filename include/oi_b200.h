@@ -1,0 +1,121 @@
+/* oi_b200.h — C ABI of the B200-native per-grid-cell GP regression hot path.
+ *
+ * Drop-in boundary for /root/reference/2021_paper_production/GPR_CS2S3.py.  The reference has no
+ * FFI/plugin interface; its seam is the Python function GPR3D(index, opt) (GPR_CS2S3.py:143-191)
+ * called once per cell from the per-rank loops (:258-261 and :317-319) and reading the module
+ * globals set up at :201-246.  A whole day is passed in one call because batching is the point:
+ *
+ *   reference                                          this ABI
+ *   ---------                                          --------
+ *   x_train,y_train,t_train,z  (:238-241)              oi_set_observations()
+ *   X = ice-cell coordinates   (:244)                  oi_set_cells()
+ *   X_tree.query_ball_point    (:159, :245-246)        oi_gather_neighbours() / oi_get_neighbours()
+ *   SMLII(hypers, x, y, mX)    (:107-141)              oi_nlml_grad()
+ *   GPR3D(index, opt=True)     (:143-168, :173-184)    oi_run(OI_MODE_FIT) / oi_gpr_day()
+ *   GPR3D(index, opt=False)    (:169-172, :185-186)    oi_run(OI_MODE_PREDICT) with hypers_in
+ *   results tuple (:184)                               out[n_cells][8] = fs, sfs2(std), lZ, lx, ly, lt, sf2, sn2
+ *
+ * Conventions: all pointers are HOST pointers to C-contiguous arrays; the library owns every
+ * device allocation behind the opaque handle.  One handle per GPU; a handle is not thread-safe;
+ * calls are synchronous.  Return value 0 = ok, negative = error (oi_last_error() gives the text).
+ * A numerical failure inside one cell (non-positive Cholesky pivot) is DATA, not an error: that
+ * cell gets NaN outputs (GPR_CS2S3.py:187-191) and status 3, the call still returns 0.
+ * There is no CPU fallback: every entry point fails with OI_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef OI_B200_H
+#define OI_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct oi_handle oi_handle;
+
+enum { OI_OK = 0, OI_ERR_ARG = -1, OI_ERR_CUDA = -2, OI_ERR_STATE = -3, OI_ERR_NOMEM = -4 };
+
+/* mode */
+enum { OI_MODE_FIT = 0,      /* GPR3D(index, opt=True):  fit by CG then predict  */
+       OI_MODE_PREDICT = 1   /* GPR3D(index, opt=False): predict with hypers_in   */ };
+/* gradient convention of SMLII: the reference's components 3 and 4 are twice the true derivative
+ * (GPR_CS2S3.py:135-138).  REFERENCE reproduces that; EXACT gives the true gradient. */
+enum { OI_GRAD_REFERENCE = 0, OI_GRAD_EXACT = 1 };
+/* per-cell status (scipy's warnflag where it applies) */
+enum { OI_CELL_OK = 0, OI_CELL_MAXITER = 1, OI_CELL_LINESEARCH = 2, OI_CELL_CHOL_FAIL = 3, OI_CELL_NO_OBS = 4,
+       OI_CELL_NAN = 5 };
+
+typedef struct oi_params {
+    double radius_m;        /* search radius in metres            (radius*1000, GPR_CS2S3.py:159, :208) */
+    double t_pred;          /* prediction time coordinate          (T_mid, :207, :164)                  */
+    double prior_mean;      /* constant prior mean                 (mean, :212, :163)                   */
+    int32_t n_hyp;          /* len(x0): 5 or 6                     (:217 has 6, the last one is dead)    */
+    int32_t mode;           /* OI_MODE_*                                                                */
+    int32_t grad_convention;/* OI_GRAD_*                                                                */
+    int32_t maxiter;        /* 0 => 200*n_hyp (scipy default)                                           */
+    double x0[6];           /* initial LOG hyperparameters         (:217)                               */
+    double gtol;            /* 0 => 1e-5 (scipy default)                                                */
+    double scratch_gib;     /* device scratch budget for the lockstep batch, 0 => automatic             */
+    int32_t max_active;     /* maximum cells evaluated per lockstep iteration, 0 => automatic           */
+    int32_t reserved;
+} oi_params;
+
+typedef struct oi_stats {
+    double ms_total;        /* device time of the last oi_run (CUDA events)                              */
+    double ms_gather;       /* neighbour gather part                                                     */
+    double flops;           /* algorithmic FP64 flops of the last oi_run (SURVEY.md §8d formula)          */
+    int64_t n_evals;        /* total NLML+gradient evaluations                                           */
+    int64_t n_launches;     /* kernels launched                                                          */
+    int64_t n_iterations;   /* lockstep iterations                                                       */
+    int64_t sum_n;          /* sum of neighbour counts                                                   */
+    double ms_factor;       /* device time inside the Cholesky/TRTRI/LAUUM kernels (CUDA events)          */
+    double flops_factor;    /* algorithmic flops of those kernels                                        */
+    double ms_build, ms_chol, ms_fwd, ms_trtri, ms_alpha, ms_lauum, ms_finalize;  /* per kernel family   */
+    double flops_chol, flops_trtri, flops_lauum;   /* n^3/3 each per evaluation            */
+    int64_t launches_chol, launches_trtri, launches_lauum;
+} oi_stats;
+
+int  oi_version(void);
+const char* oi_last_error(void);
+
+int  oi_create(int device, oi_handle** out);
+/* Launch on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g. torch's current stream, so
+ * that the caller's CUDA events bracket the kernels.  NULL restores the handle's own stream. */
+int  oi_set_stream(oi_handle* h, void* cuda_stream);
+void oi_destroy(oi_handle* h);
+
+/* Observations of the day window: x_train, y_train, t_train, z (GPR_CS2S3.py:238-241). */
+int oi_set_observations(oi_handle* h, const double* x, const double* y, const double* t, const double* z,
+                        int64_t n_obs);
+/* Target cells X[n_cells][2] (GPR_CS2S3.py:244). */
+int oi_set_cells(oi_handle* h, const double* X, int64_t n_cells);
+
+/* Kernel (1): for every cell the set {i : dx*dx + dy*dy <= r*r} (inclusive, :159), as CSR in
+ * ascending observation order.  counts_out[n_cells] may be NULL. */
+int oi_gather_neighbours(oi_handle* h, double radius_m, int32_t* counts_out);
+/* Copy the CSR back: offsets[n_cells+1], indices[sum n] (either may be NULL). */
+int oi_get_neighbours(oi_handle* h, int64_t* offsets, int32_t* indices);
+
+/* SMLII (GPR_CS2S3.py:107-141) for every cell at its own LOG hyperparameters hypers[n_cells][n_hyp]:
+ * nlz_out[n_cells], grad_out[n_cells][n_hyp].  Needs oi_gather_neighbours first. */
+int oi_nlml_grad(oi_handle* h, const double* hypers, int32_t n_hyp, double prior_mean, int32_t grad_convention,
+                 double* nlz_out, double* grad_out);
+
+/* Fit+predict or predict-only on the resident day (needs observations, cells and neighbours).
+ * hypers_in[n_cells][5] (natural units lx,ly,lt,sf2,sn2) is read only in OI_MODE_PREDICT.
+ * Results stay on the device until oi_get_results. */
+int oi_run(oi_handle* h, const oi_params* p, const double* hypers_in);
+/* out[n_cells][8]; nfev_out/status_out/n_out[n_cells] may be NULL. */
+int oi_get_results(oi_handle* h, double* out, int32_t* n_out, int32_t* nfev_out, int32_t* status_out);
+int oi_get_stats(oi_handle* h, oi_stats* s);
+
+/* The whole day in one call: set_observations + set_cells + gather + run + get_results. */
+int oi_gpr_day(oi_handle* h, const double* x, const double* y, const double* t, const double* z, int64_t n_obs,
+               const double* X, int64_t n_cells, const oi_params* p, const double* hypers_in,
+               double* out, int32_t* n_out, int32_t* nfev_out, int32_t* status_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OI_B200_H */

@@ -1,0 +1,73 @@
+"""ctypes binding of the C ABI in include/oi_b200.h (liboi_b200.so, built in-tree by
+``optimalinterpolation_b200/csrc/Makefile``).  There is no CPU fallback: a missing library or a
+missing sm_100 device raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "liboi_b200.so")
+
+EXPORTS = ("oi_version", "oi_last_error", "oi_create", "oi_destroy", "oi_set_observations", "oi_set_cells",
+           "oi_gather_neighbours", "oi_get_neighbours", "oi_nlml_grad", "oi_run", "oi_get_results",
+           "oi_get_stats", "oi_gpr_day", "oi_set_stream")
+
+
+class OiParams(C.Structure):
+    _fields_ = [("radius_m", C.c_double), ("t_pred", C.c_double), ("prior_mean", C.c_double),
+                ("n_hyp", C.c_int32), ("mode", C.c_int32), ("grad_convention", C.c_int32), ("maxiter", C.c_int32),
+                ("x0", C.c_double * 6), ("gtol", C.c_double), ("scratch_gib", C.c_double),
+                ("max_active", C.c_int32), ("reserved", C.c_int32)]
+
+
+class OiStats(C.Structure):
+    _fields_ = [("ms_total", C.c_double), ("ms_gather", C.c_double), ("flops", C.c_double),
+                ("n_evals", C.c_int64), ("n_launches", C.c_int64), ("n_iterations", C.c_int64),
+                ("sum_n", C.c_int64), ("ms_factor", C.c_double), ("flops_factor", C.c_double),
+                ("ms_build", C.c_double), ("ms_chol", C.c_double), ("ms_fwd", C.c_double), ("ms_trtri", C.c_double),
+                ("ms_alpha", C.c_double), ("ms_lauum", C.c_double), ("ms_finalize", C.c_double),
+                ("flops_chol", C.c_double), ("flops_trtri", C.c_double), ("flops_lauum", C.c_double),
+                ("launches_chol", C.c_int64), ("launches_trtri", C.c_int64), ("launches_lauum", C.c_int64)]
+
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile liboi_b200.so for sm_100a with nvcc (works without a GPU)."""
+    import subprocess
+    out = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
+    if verbose or out.returncode:
+        print(out.stdout, out.stderr)
+    if out.returncode:
+        raise RuntimeError("building liboi_b200.so failed")
+    return LIB_PATH
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(optimalinterpolation_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, dp, ip, lp = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+    L.oi_version.restype = C.c_int
+    L.oi_last_error.restype = C.c_char_p
+    L.oi_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.oi_destroy.argtypes = [vp]
+    L.oi_set_stream.argtypes = [vp, vp]
+    L.oi_destroy.restype = None
+    L.oi_set_observations.argtypes = [vp, dp, dp, dp, dp, C.c_int64]
+    L.oi_set_cells.argtypes = [vp, dp, C.c_int64]
+    L.oi_gather_neighbours.argtypes = [vp, C.c_double, ip]
+    L.oi_get_neighbours.argtypes = [vp, lp, ip]
+    L.oi_nlml_grad.argtypes = [vp, dp, C.c_int32, C.c_double, C.c_int32, dp, dp]
+    L.oi_run.argtypes = [vp, C.POINTER(OiParams), dp]
+    L.oi_get_results.argtypes = [vp, dp, ip, ip, ip]
+    L.oi_get_stats.argtypes = [vp, C.POINTER(OiStats)]
+    L.oi_gpr_day.argtypes = [vp, dp, dp, dp, dp, C.c_int64, dp, C.c_int64, C.POINTER(OiParams), dp, dp, ip, ip, ip]
+    _lib = L
+    return L

@@ -1,0 +1,461 @@
+// Host side of the C ABI (include/oi_b200.h): device buffers, the lockstep batch scheduler and
+// the entry points.  Replaces the reference's per-rank cell loop (GPR_CS2S3.py:258-261, :317-319):
+// instead of one cell at a time per MPI rank, every lockstep iteration evaluates SMLII (or the
+// posterior) for ALL active cells at once, each cell at the point its own optimiser asked for.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/oi_b200.h"
+#include "oi_types.h"
+#include "oi_launch.h"
+#include "cg_scipy.h"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? OI_ERR_NOMEM : OI_ERR_CUDA,              \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                       \
+    } while (0)
+
+struct oi_handle {
+    int device = 0;
+    cudaStream_t st = nullptr, own_st = nullptr;
+    // observations
+    double *ox = nullptr, *oy = nullptr, *ot = nullptr, *oz = nullptr;
+    int64_t n_obs = 0, obs_cap = 0;
+    // cells
+    double* X = nullptr;
+    int64_t n_cells = 0, cell_cap = 0;
+    // neighbours (CSR)
+    int* counts = nullptr; long long* offsets = nullptr; int* indices = nullptr;
+    long long total = 0, idx_cap = 0;
+    bool have_nbr = false;
+    std::vector<int> h_counts;
+    std::vector<long long> h_offsets;
+    // packed per-cell coordinates
+    double *px = nullptr, *py = nullptr, *pt = nullptr, *pr = nullptr;
+    // per-cell state
+    OiCellArrays ca{};
+    // lockstep batch
+    char* arena = nullptr; size_t arena_bytes = 0;
+    OiSlot* d_slots = nullptr; OiSlot* h_slots = nullptr;
+    int *d_slot_phase = nullptr, *h_slot_phase = nullptr, *d_fail = nullptr;
+    int slot_cap = 0;
+    cudaEvent_t ev[10]{};
+    oi_stats stats{};
+    bool have_results = false;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static size_t slot_bytes(int n) {
+    size_t N = (n + OI_NB - 1) / OI_NB, npad = N * OI_NB;
+    size_t b = align_up(npad * npad * 8, 256);
+    b += align_up(N * OI_TILE * 8, 256);
+    b += align_up(3 * npad * 8, 256);
+    b += align_up((N + 8 + 5 * N * (N + 1) / 2) * 8, 256);
+    return b;
+}
+
+extern "C" int oi_version(void) { return 100; }
+extern "C" const char* oi_last_error(void) { return g_err.c_str(); }
+
+extern "C" int oi_create(int device, oi_handle** out) {
+    if (!out) return fail(OI_ERR_ARG, "oi_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(OI_ERR_CUDA, std::string("oi_create: no CUDA device (") + cudaGetErrorString(e) +
+                                     "); this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(OI_ERR_ARG, "oi_create: bad device index");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10)
+        return fail(OI_ERR_CUDA, "oi_create: device is sm_" + std::to_string(p.major * 10 + p.minor) +
+                                     ", kernels are built for sm_100a only");
+    oi_handle* h = new oi_handle();
+    h->device = device;
+    CK(cudaStreamCreate(&h->own_st));
+    h->st = h->own_st;
+    for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
+    *out = h;
+    return OI_OK;
+}
+
+extern "C" int oi_set_stream(oi_handle* h, void* cuda_stream) {
+    if (!h) return fail(OI_ERR_ARG, "oi_set_stream: NULL handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->st));
+    h->st = cuda_stream ? (cudaStream_t)cuda_stream : h->own_st;
+    return OI_OK;
+}
+
+static void free_cells(oi_handle* h) {
+    cudaFree(h->X); cudaFree(h->counts); cudaFree(h->offsets);
+    cudaFree(h->ca.hyp); cudaFree(h->ca.phase); cudaFree(h->ca.out); cudaFree(h->ca.nfev); cudaFree(h->ca.status);
+    cudaFree(h->ca.evf); cudaFree(h->ca.evg); cudaFree(h->ca.cg);
+    h->X = nullptr; h->counts = nullptr; h->offsets = nullptr; h->ca = OiCellArrays{}; h->cell_cap = 0;
+}
+
+extern "C" void oi_destroy(oi_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->ox); cudaFree(h->oy); cudaFree(h->ot); cudaFree(h->oz);
+    free_cells(h);
+    cudaFree(h->indices); cudaFree(h->px); cudaFree(h->py); cudaFree(h->pt); cudaFree(h->pr);
+    cudaFree(h->arena); cudaFree(h->d_slots); cudaFree(h->d_slot_phase); cudaFree(h->d_fail);
+    cudaFreeHost(h->h_slots); cudaFreeHost(h->h_slot_phase);
+    for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    if (h->own_st) cudaStreamDestroy(h->own_st);
+    delete h;
+}
+
+extern "C" int oi_set_observations(oi_handle* h, const double* x, const double* y, const double* t, const double* z,
+                                   int64_t n_obs) {
+    if (!h || !x || !y || !t || !z || n_obs <= 0 || n_obs > 0x7fffffff) return fail(OI_ERR_ARG, "oi_set_observations: bad argument");
+    CK(cudaSetDevice(h->device));
+    if (n_obs > h->obs_cap) {
+        cudaFree(h->ox); cudaFree(h->oy); cudaFree(h->ot); cudaFree(h->oz);
+        CK(cudaMalloc(&h->ox, n_obs * 8)); CK(cudaMalloc(&h->oy, n_obs * 8));
+        CK(cudaMalloc(&h->ot, n_obs * 8)); CK(cudaMalloc(&h->oz, n_obs * 8));
+        h->obs_cap = n_obs;
+    }
+    h->n_obs = n_obs;
+    CK(cudaMemcpyAsync(h->ox, x, n_obs * 8, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->oy, y, n_obs * 8, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->ot, t, n_obs * 8, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->oz, z, n_obs * 8, cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    h->have_nbr = false; h->have_results = false;
+    return OI_OK;
+}
+
+extern "C" int oi_set_cells(oi_handle* h, const double* X, int64_t n_cells) {
+    if (!h || !X || n_cells <= 0 || n_cells > 0x3fffffff) return fail(OI_ERR_ARG, "oi_set_cells: bad argument");
+    CK(cudaSetDevice(h->device));
+    if (n_cells > h->cell_cap) {
+        free_cells(h);
+        size_t c = (size_t)n_cells;
+        CK(cudaMalloc(&h->X, c * 16)); CK(cudaMalloc(&h->counts, c * 4)); CK(cudaMalloc(&h->offsets, (c + 1) * 8));
+        CK(cudaMalloc(&h->ca.hyp, c * 40)); CK(cudaMalloc(&h->ca.phase, c * 4)); CK(cudaMalloc(&h->ca.out, c * 64));
+        CK(cudaMalloc(&h->ca.nfev, c * 4)); CK(cudaMalloc(&h->ca.status, c * 4)); CK(cudaMalloc(&h->ca.evf, c * 8));
+        CK(cudaMalloc(&h->ca.evg, c * 8 * OI_MAXH)); CK(cudaMalloc(&h->ca.cg, c * sizeof(OiCgState)));
+        h->cell_cap = n_cells;
+    }
+    h->ca.X = h->X;
+    h->n_cells = n_cells;
+    CK(cudaMemcpyAsync(h->X, X, n_cells * 16, cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    h->have_nbr = false; h->have_results = false;
+    return OI_OK;
+}
+
+extern "C" int oi_gather_neighbours(oi_handle* h, double radius_m, int32_t* counts_out) {
+    if (!h || !(radius_m >= 0)) return fail(OI_ERR_ARG, "oi_gather_neighbours: bad argument");
+    if (h->n_obs <= 0 || h->n_cells <= 0) return fail(OI_ERR_STATE, "oi_gather_neighbours: set observations and cells first");
+    CK(cudaSetDevice(h->device));
+    const double r2 = radius_m * radius_m;
+    const int nc = (int)h->n_cells, no = (int)h->n_obs;
+    CK(cudaEventRecord(h->ev[8], h->st));
+    oi_launch_count(h->ox, h->oy, no, h->X, nc, r2, h->counts, h->st);
+    oi_launch_scan(h->counts, nc, h->offsets, h->st);
+    CK(cudaGetLastError());
+    long long total = 0;
+    CK(cudaMemcpyAsync(&total, h->offsets + nc, 8, cudaMemcpyDeviceToHost, h->st));
+    h->h_counts.resize(nc);
+    CK(cudaMemcpyAsync(h->h_counts.data(), h->counts, (size_t)nc * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (total > h->idx_cap) {
+        cudaFree(h->indices); cudaFree(h->px); cudaFree(h->py); cudaFree(h->pt); cudaFree(h->pr);
+        size_t c = (size_t)std::max<long long>(total, 1);
+        CK(cudaMalloc(&h->indices, c * 4));
+        CK(cudaMalloc(&h->px, c * 8)); CK(cudaMalloc(&h->py, c * 8)); CK(cudaMalloc(&h->pt, c * 8)); CK(cudaMalloc(&h->pr, c * 8));
+        h->idx_cap = total;
+    }
+    h->total = total;
+    h->h_offsets.assign((size_t)nc + 1, 0);
+    for (int c = 0; c < nc; c++) h->h_offsets[c + 1] = h->h_offsets[c] + h->h_counts[c];
+    if (total > 0) oi_launch_fill(h->ox, h->oy, no, h->X, nc, r2, h->offsets, h->indices, h->st);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[9], h->st));
+    CK(cudaStreamSynchronize(h->st));
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev[8], h->ev[9]);
+    h->stats.ms_gather = ms;
+    h->stats.sum_n = total;
+    h->have_nbr = true; h->have_results = false;
+    if (counts_out) std::memcpy(counts_out, h->h_counts.data(), (size_t)nc * 4);
+    return OI_OK;
+}
+
+extern "C" int oi_get_neighbours(oi_handle* h, int64_t* offsets, int32_t* indices) {
+    if (!h) return fail(OI_ERR_ARG, "oi_get_neighbours: NULL handle");
+    if (!h->have_nbr) return fail(OI_ERR_STATE, "oi_get_neighbours: call oi_gather_neighbours first");
+    CK(cudaSetDevice(h->device));
+    if (offsets) CK(cudaMemcpy(offsets, h->offsets, (size_t)(h->n_cells + 1) * 8, cudaMemcpyDeviceToHost));
+    if (indices && h->total > 0) CK(cudaMemcpy(indices, h->indices, (size_t)h->total * 4, cudaMemcpyDeviceToHost));
+    return OI_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// the lockstep batch scheduler
+// ------------------------------------------------------------------------------------------
+static int ensure_batch_buffers(oi_handle* h, size_t want_arena, int want_slots) {
+    if (want_arena > h->arena_bytes) {
+        cudaFree(h->arena); h->arena = nullptr; h->arena_bytes = 0;
+        CK(cudaMalloc(&h->arena, want_arena));
+        h->arena_bytes = want_arena;
+    }
+    if (want_slots > h->slot_cap) {
+        cudaFree(h->d_slots); cudaFree(h->d_slot_phase); cudaFree(h->d_fail);
+        cudaFreeHost(h->h_slots); cudaFreeHost(h->h_slot_phase);
+        CK(cudaMalloc(&h->d_slots, (size_t)want_slots * sizeof(OiSlot)));
+        CK(cudaMalloc(&h->d_slot_phase, (size_t)want_slots * 4));
+        CK(cudaMalloc(&h->d_fail, (size_t)want_slots * 4));
+        CK(cudaMallocHost(&h->h_slots, (size_t)want_slots * sizeof(OiSlot)));
+        CK(cudaMallocHost(&h->h_slot_phase, (size_t)want_slots * 4));
+        h->slot_cap = want_slots;
+    }
+    return OI_OK;
+}
+
+// Runs lockstep iterations until every cell with observations reaches OI_PH_DONE.
+// h_phase: host copy of the initial per-cell phase (already uploaded to ca.phase).
+static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunConst& rc, double t_pred,
+                        double scratch_gib, int max_active) {
+    const int nc = (int)h->n_cells;
+    std::vector<int> pending;
+    pending.reserve(nc);
+    size_t biggest = 0;
+    for (int c = 0; c < nc; c++)
+        if (h->h_counts[c] > 0 && h_phase[c] != OI_PH_DONE) { pending.push_back(c); biggest = std::max(biggest, slot_bytes(h->h_counts[c])); }
+    // largest cells first: cost-sorted ragged batches (cost ~ n^3)
+    std::stable_sort(pending.begin(), pending.end(), [&](int a, int b) { return h->h_counts[a] > h->h_counts[b]; });
+    if (pending.empty()) return OI_OK;
+    if (max_active <= 0) max_active = 2048;
+    max_active = std::min<int>(max_active, 65535);
+    size_t want;
+    if (scratch_gib > 0) want = (size_t)(scratch_gib * 1073741824.0);
+    else {
+        size_t fr = 0, tot = 0;
+        CK(cudaMemGetInfo(&fr, &tot));
+        fr += h->arena_bytes;
+        want = std::min<size_t>((size_t)(fr * 0.8), (size_t)64 << 30);
+    }
+    size_t all = 0;
+    for (int c : pending) all += slot_bytes(h->h_counts[c]);
+    want = std::min(want, all);          // never more than everything resident
+    want = std::max(want, biggest);
+    int rcode = ensure_batch_buffers(h, want, std::min<int>(max_active, (int)pending.size()));
+    if (rcode) return rcode;
+
+    OiPacked pk{h->px, h->py, h->pt, h->pr};
+    std::vector<int> active;
+    size_t used = 0, next = 0;
+    double ms_factor = 0;
+    while (true) {
+        while (next < pending.size() && (int)active.size() < max_active) {
+            size_t need = slot_bytes(h->h_counts[pending[next]]);
+            if (used + need > h->arena_bytes) break;
+            used += need; active.push_back(pending[next++]);
+        }
+        if (active.empty()) {
+            if (next < pending.size()) return fail(OI_ERR_NOMEM, "run_lockstep: scratch arena too small for one cell");
+            break;
+        }
+        const int A = (int)active.size();
+        size_t off = 0;
+        int Nmax = 0;
+        double fl = 0, flf = 0, flf_chol = 0, flf_fit = 0;
+        int64_t nev = 0;
+        for (int a = 0; a < A; a++) {
+            int c = active[a], n = h->h_counts[c];
+            int N = (n + OI_NB - 1) / OI_NB, npad = N * OI_NB;
+            OiSlot& s = h->h_slots[a];
+            s.M = (double*)(h->arena + off); off += align_up((size_t)npad * npad * 8, 256);
+            s.Dinv = (double*)(h->arena + off); off += align_up((size_t)N * OI_TILE * 8, 256);
+            s.vec = (double*)(h->arena + off); off += align_up((size_t)3 * npad * 8, 256);
+            s.part = (double*)(h->arena + off); off += align_up((size_t)(N + 8 + 5 * N * (N + 1) / 2) * 8, 256);
+            s.fail = h->d_fail + a;
+            s.pt_off = 0;   // filled below from the CSR offsets
+            s.cell = c; s.n = n; s.npad = npad; s.N = N;
+            Nmax = std::max(Nmax, N);
+            double dn = n;
+            flf_chol += dn * dn * dn / 3;
+            if (h_phase[c] == OI_PH_PREDICT) { fl += dn * dn * dn / 3 + 19 * dn * dn; flf += dn * dn * dn / 3; }
+            else { fl += dn * dn * dn + 22 * dn * dn; flf += dn * dn * dn; flf_fit += dn * dn * dn; nev++; }
+        }
+        for (int a = 0; a < A; a++) h->h_slots[a].pt_off = h->h_offsets[active[a]];
+        CK(cudaMemcpyAsync(h->d_slots, h->h_slots, (size_t)A * sizeof(OiSlot), cudaMemcpyHostToDevice, h->st));
+        CK(cudaEventRecord(h->ev[0], h->st));
+        oi_launch_build(h->d_slots, A, Nmax, h->ca, pk, h->st);
+        CK(cudaEventRecord(h->ev[1], h->st));
+        for (int k = 0; k < Nmax; k++) {
+            oi_launch_chol_update(h->d_slots, A, Nmax, k, h->st);
+            oi_launch_chol_panel(h->d_slots, A, Nmax, k, h->st);
+        }
+        CK(cudaEventRecord(h->ev[2], h->st));
+        oi_launch_fwd(h->d_slots, A, h->ca, pk, t_pred, h->st);
+        CK(cudaEventRecord(h->ev[3], h->st));
+        for (int d = 1; d < Nmax; d++) oi_launch_trtri(h->d_slots, A, Nmax, d, h->ca.phase, h->st);
+        CK(cudaEventRecord(h->ev[4], h->st));
+        oi_launch_alpha(h->d_slots, A, Nmax, h->ca.phase, h->st);
+        CK(cudaEventRecord(h->ev[5], h->st));
+        oi_launch_lauum_trace(h->d_slots, A, Nmax, h->ca, pk, h->st);
+        CK(cudaEventRecord(h->ev[6], h->st));
+        oi_launch_finalize(h->d_slots, A, h->ca, rc, h->d_slot_phase, h->st);
+        CK(cudaEventRecord(h->ev[7], h->st));
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h->h_slot_phase, h->d_slot_phase, (size_t)A * 4, cudaMemcpyDeviceToHost, h->st));
+        CK(cudaStreamSynchronize(h->st));
+        float m[7];
+        for (int q = 0; q < 7; q++) cudaEventElapsedTime(&m[q], h->ev[q], h->ev[q + 1]);
+        h->stats.ms_build += m[0]; h->stats.ms_chol += m[1]; h->stats.ms_fwd += m[2]; h->stats.ms_trtri += m[3];
+        h->stats.ms_alpha += m[4]; h->stats.ms_lauum += m[5]; h->stats.ms_finalize += m[6];
+        ms_factor += m[1] + m[3] + m[5];
+        h->stats.flops += fl; h->stats.flops_factor += flf; h->stats.n_evals += nev;
+        h->stats.flops_chol += flf_chol; h->stats.flops_trtri += flf_fit / 3; h->stats.flops_lauum += flf_fit / 3;
+        h->stats.launches_chol += 2 * Nmax - 1; h->stats.launches_trtri += std::max(0, Nmax - 1); h->stats.launches_lauum += 1;
+        h->stats.n_iterations++;
+        h->stats.n_launches += 1 + Nmax + std::max(0, Nmax - 1) + 1 + std::max(0, Nmax - 1) + 2 + 1;
+        // retire finished cells, keep the rest in (descending n) order
+        size_t w = 0;
+        for (int a = 0; a < A; a++) {
+            int c = active[a];
+            h_phase[c] = h->h_slot_phase[a];
+            if (h_phase[c] == OI_PH_DONE) used -= slot_bytes(h->h_counts[c]);
+            else active[w++] = c;
+        }
+        active.resize(w);
+    }
+    h->stats.ms_factor += ms_factor;
+    return OI_OK;
+}
+
+static int pack_points(oi_handle* h, double mean) {
+    oi_launch_pack(h->indices, h->total, h->ox, h->oy, h->ot, h->oz, mean, h->px, h->py, h->pt, h->pr, h->st);
+    CK(cudaGetLastError());
+    return OI_OK;
+}
+
+static void reset_stats(oi_handle* h) {
+    double g = h->stats.ms_gather; int64_t sn = h->stats.sum_n;
+    h->stats = oi_stats{};
+    h->stats.ms_gather = g; h->stats.sum_n = sn;
+}
+
+extern "C" int oi_nlml_grad(oi_handle* h, const double* hypers, int32_t n_hyp, double prior_mean, int32_t grad_convention,
+                            double* nlz_out, double* grad_out) {
+    if (!h || !hypers || !nlz_out || !grad_out || n_hyp < 5 || n_hyp > OI_MAXH) return fail(OI_ERR_ARG, "oi_nlml_grad: bad argument");
+    if (!h->have_nbr) return fail(OI_ERR_STATE, "oi_nlml_grad: call oi_gather_neighbours first");
+    CK(cudaSetDevice(h->device));
+    const int nc = (int)h->n_cells;
+    std::vector<double> hyp((size_t)nc * 5);
+    std::vector<int> phase(nc);
+    for (int c = 0; c < nc; c++) {
+        for (int q = 0; q < 5; q++) hyp[(size_t)c * 5 + q] = std::exp(hypers[(size_t)c * n_hyp + q]);   // GPR_CS2S3.py:120-122
+        phase[c] = h->h_counts[c] > 0 ? OI_PH_EVAL : OI_PH_DONE;
+    }
+    CK(cudaMemcpyAsync(h->ca.hyp, hyp.data(), hyp.size() * 8, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->ca.phase, phase.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, h->st));
+    int r = pack_points(h, prior_mean);
+    if (r) return r;
+    CK(cudaStreamSynchronize(h->st));
+    OiRunConst rc{};
+    rc.mean = prior_mean; rc.gtol = 1e-5; rc.n_hyp = n_hyp; rc.grad_convention = grad_convention; rc.maxiter = 0;
+    reset_stats(h);
+    r = run_lockstep(h, phase, rc, 0.0, 0.0, 0);
+    if (r) return r;
+    std::vector<double> f(nc), g((size_t)nc * OI_MAXH);
+    CK(cudaMemcpy(f.data(), h->ca.evf, (size_t)nc * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(g.data(), h->ca.evg, g.size() * 8, cudaMemcpyDeviceToHost));
+    for (int c = 0; c < nc; c++) {
+        bool none = h->h_counts[c] <= 0;
+        nlz_out[c] = none ? NAN : f[c];
+        for (int q = 0; q < n_hyp; q++) grad_out[(size_t)c * n_hyp + q] = none ? NAN : g[(size_t)c * OI_MAXH + q];
+    }
+    return OI_OK;
+}
+
+extern "C" int oi_run(oi_handle* h, const oi_params* p, const double* hypers_in) {
+    if (!h || !p) return fail(OI_ERR_ARG, "oi_run: NULL argument");
+    if (p->mode != OI_MODE_FIT && p->mode != OI_MODE_PREDICT) return fail(OI_ERR_ARG, "oi_run: bad mode");
+    if (p->mode == OI_MODE_PREDICT && !hypers_in) return fail(OI_ERR_ARG, "oi_run: predict mode needs hypers_in");
+    if (p->mode == OI_MODE_FIT && (p->n_hyp < 5 || p->n_hyp > OI_MAXH)) return fail(OI_ERR_ARG, "oi_run: n_hyp must be 5 or 6");
+    if (!h->have_nbr) return fail(OI_ERR_STATE, "oi_run: call oi_gather_neighbours first");
+    CK(cudaSetDevice(h->device));
+    const int nc = (int)h->n_cells;
+    reset_stats(h);
+    CK(cudaEventRecord(h->ev[8], h->st));
+    int r = pack_points(h, p->prior_mean);
+    if (r) return r;
+    OiRunConst rc{};
+    rc.mean = p->prior_mean; rc.gtol = p->gtol > 0 ? p->gtol : 1e-5; rc.n_hyp = p->mode == OI_MODE_FIT ? p->n_hyp : 5;
+    rc.grad_convention = p->grad_convention; rc.maxiter = p->maxiter;
+    for (int q = 0; q < OI_MAXH; q++) rc.x0[q] = p->x0[q];
+    std::vector<int> phase(nc);
+    // cells without observations: NaN tuple, status NO_OBS (the reference would raise inside pdist)
+    std::vector<double> out0((size_t)nc * 8, NAN);
+    std::vector<int> st0(nc), nf0(nc, 0);
+    for (int c = 0; c < nc; c++) {
+        bool none = h->h_counts[c] <= 0;
+        phase[c] = none ? OI_PH_DONE : (p->mode == OI_MODE_FIT ? OI_PH_FIT : OI_PH_PREDICT);
+        st0[c] = none ? OI_CELL_NO_OBS : OI_CELL_OK;
+    }
+    CK(cudaMemcpyAsync(h->ca.out, out0.data(), out0.size() * 8, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->ca.status, st0.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->ca.nfev, nf0.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->ca.phase, phase.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, h->st));
+    if (p->mode == OI_MODE_FIT) {
+        oi_launch_cg_init(h->ca, nc, rc, h->st);
+        CK(cudaGetLastError());
+    } else {
+        CK(cudaMemcpyAsync(h->ca.hyp, hypers_in, (size_t)nc * 40, cudaMemcpyHostToDevice, h->st));
+    }
+    CK(cudaStreamSynchronize(h->st));   // staging vectors go out of scope below
+    r = run_lockstep(h, phase, rc, p->t_pred, p->scratch_gib, p->max_active);
+    if (r) return r;
+    CK(cudaEventRecord(h->ev[9], h->st));
+    CK(cudaStreamSynchronize(h->st));
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev[8], h->ev[9]);
+    h->stats.ms_total = ms;
+    h->have_results = true;
+    return OI_OK;
+}
+
+extern "C" int oi_get_results(oi_handle* h, double* out, int32_t* n_out, int32_t* nfev_out, int32_t* status_out) {
+    if (!h || !out) return fail(OI_ERR_ARG, "oi_get_results: NULL argument");
+    if (!h->have_results) return fail(OI_ERR_STATE, "oi_get_results: call oi_run first");
+    CK(cudaSetDevice(h->device));
+    const size_t nc = (size_t)h->n_cells;
+    CK(cudaMemcpy(out, h->ca.out, nc * 64, cudaMemcpyDeviceToHost));
+    if (nfev_out) CK(cudaMemcpy(nfev_out, h->ca.nfev, nc * 4, cudaMemcpyDeviceToHost));
+    if (status_out) CK(cudaMemcpy(status_out, h->ca.status, nc * 4, cudaMemcpyDeviceToHost));
+    if (n_out) std::memcpy(n_out, h->h_counts.data(), nc * 4);
+    return OI_OK;
+}
+
+extern "C" int oi_get_stats(oi_handle* h, oi_stats* s) {
+    if (!h || !s) return fail(OI_ERR_ARG, "oi_get_stats: NULL argument");
+    *s = h->stats;
+    return OI_OK;
+}
+
+extern "C" int oi_gpr_day(oi_handle* h, const double* x, const double* y, const double* t, const double* z, int64_t n_obs,
+                          const double* X, int64_t n_cells, const oi_params* p, const double* hypers_in,
+                          double* out, int32_t* n_out, int32_t* nfev_out, int32_t* status_out) {
+    if (!p) return fail(OI_ERR_ARG, "oi_gpr_day: NULL params");
+    int r;
+    if ((r = oi_set_observations(h, x, y, t, z, n_obs))) return r;
+    if ((r = oi_set_cells(h, X, n_cells))) return r;
+    if ((r = oi_gather_neighbours(h, p->radius_m, nullptr))) return r;
+    if ((r = oi_run(h, p, hypers_in))) return r;
+    return oi_get_results(h, out, n_out, nfev_out, status_out);
+}

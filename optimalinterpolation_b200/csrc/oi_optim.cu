@@ -1,0 +1,102 @@
+// Finalisation of one lockstep evaluation + the per-cell optimiser step (compiled with -fmad=false
+// so the optimiser's arithmetic rounds like the NumPy/Python code it restates, cg_scipy.h).
+//
+//   FIT / EVAL : nlZ and gradient as SMLII returns them (GPR_CS2S3.py:128-140), then one resume of the
+//                scipy-CG state machine (GPR_CS2S3.py:166) -> next trial hyperparameters or "converged"
+//   PREDICT    : fs, sfs2, lZ and the hyperparameters as GPR3D returns them (GPR_CS2S3.py:179-191)
+#include <cuda_runtime.h>
+#include <math.h>
+#include "oi_types.h"
+#include "oi_launch.h"
+#include "cg_scipy.h"
+
+#define LOG_2PI 1.8378770664093453   // np.log(2*np.pi)
+
+__global__ void k_cg_init(OiCellArrays ca, int n_cells, OiRunConst rc) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    OiCgState* S = (OiCgState*)ca.cg + c;
+    OiCgState L;
+    oi_cg_init(L, rc.x0, rc.n_hyp, rc.maxiter, rc.gtol);
+    double dummy[OI_MAXH] = {0, 0, 0, 0, 0, 0};
+    oi_cg_resume(L, 0.0, dummy);          // first resume only publishes x0 as the first request
+    *S = L;
+    for (int q = 0; q < 5; q++) ca.hyp[5 * (size_t)c + q] = exp(L.req_x[q]);
+}
+
+__global__ void __launch_bounds__(128) k_finalize(const OiSlot* __restrict__ slots, int A, OiCellArrays ca, OiRunConst rc,
+                                                  int* __restrict__ slot_phase) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= A) return;
+    const OiSlot s = slots[warp];
+    const int phase = ca.phase[s.cell];
+    const bool failed = *s.fail != 0;
+    double S[5] = {0, 0, 0, 0, 0};
+    if (!failed && phase != OI_PH_PREDICT) {
+        const int nt = s.N * (s.N + 1) / 2;
+        const double* tp = s.part + s.N + 8;
+        for (int t = lane; t < nt; t += 32)
+            for (int q = 0; q < 5; q++) S[q] += tp[5 * (size_t)t + q];
+        for (int q = 0; q < 5; q++)
+            for (int o = 16; o > 0; o >>= 1) S[q] += __shfl_down_sync(0xffffffffu, S[q], o);
+    }
+    if (lane != 0) return;
+    double logdet = 0.0;
+    if (!failed) for (int k = 0; k < s.N; k++) logdet += s.part[k];
+    const double quad = s.part[s.N + 0], vt = s.part[s.N + 1], vv = s.part[s.N + 2];
+    double* h = ca.hyp + 5 * (size_t)s.cell;
+    const double sf2 = h[3], sn2 = h[4];
+    int newphase = OI_PH_DONE;
+    if (phase == OI_PH_PREDICT) {
+        double* o = ca.out + 8 * (size_t)s.cell;
+        if (failed) {
+            for (int q = 0; q < 8; q++) o[q] = nan("");
+            ca.status[s.cell] = 3;
+        } else {
+            o[0] = rc.mean + vt;                                   // fs  = mean + k*^T A            (:181)
+            o[1] = sqrt(sf2 - vv);                                 // sfs2 = sqrt(k** - v^T v)       (:182)
+            o[2] = -quad / 2 - logdet - s.n * LOG_2PI / 2;         // lZ                             (:179)
+            for (int q = 0; q < 5; q++) o[3 + q] = h[q];
+        }
+    } else {
+        double f, g[OI_MAXH];
+        if (failed) {
+            f = INFINITY;
+            for (int q = 0; q < OI_MAXH; q++) g[q] = INFINITY;      // :139-140
+        } else {
+            f = quad / 2 + logdet + s.n * LOG_2PI / 2;              // :128
+            g[0] = (sf2 * S[0]) / 2; g[1] = (sf2 * S[1]) / 2; g[2] = (sf2 * S[2]) / 2;   // :134
+            g[3] = sf2 * S[3];                                      // (Q*(2*Kx)).sum()/2   :136
+            g[4] = sn2 * S[4];                                      // sn2*trace(Q)         :138
+            if (rc.grad_convention == 1) { g[3] /= 2; g[4] /= 2; }  // true derivatives
+            g[5] = 0.0;
+        }
+        if (phase == OI_PH_EVAL) {
+            ca.evf[s.cell] = f;
+            for (int q = 0; q < OI_MAXH; q++) ca.evg[OI_MAXH * (size_t)s.cell + q] = g[q];
+        } else {
+            OiCgState* Sg = (OiCgState*)ca.cg + s.cell;
+            OiCgState L = *Sg;
+            int r = oi_cg_resume(L, f, g);
+            *Sg = L;
+            if (r == OI_CG_NEED_EVAL) {
+                for (int q = 0; q < 5; q++) h[q] = exp(L.req_x[q]);
+                newphase = OI_PH_FIT;
+            } else {
+                for (int q = 0; q < 5; q++) h[q] = exp(L.xk[q]);    // np.exp(res.x), status ignored (:166)
+                ca.nfev[s.cell] = L.nfev;
+                ca.status[s.cell] = L.status == 3 ? 5 : L.status;
+                newphase = OI_PH_PREDICT;
+            }
+        }
+    }
+    ca.phase[s.cell] = newphase;
+    slot_phase[warp] = newphase;
+}
+
+void oi_launch_cg_init(OiCellArrays ca, int n_cells, OiRunConst rc, cudaStream_t st) {
+    k_cg_init<<<(n_cells + 127) / 128, 128, 0, st>>>(ca, n_cells, rc);
+}
+void oi_launch_finalize(const OiSlot* slots, int A, OiCellArrays ca, OiRunConst rc, int* slot_phase, cudaStream_t st) {
+    k_finalize<<<(A * 32 + 127) / 128, 128, 0, st>>>(slots, A, ca, rc, slot_phase);
+}

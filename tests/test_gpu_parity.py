@@ -1,0 +1,180 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): neighbour index sets bit-exact; at fixed hyperparameters
+posterior mean, std and NLML (and the gradient) within 1e-9 relative; with fitted hyperparameters
+per-cell NLML within 1e-6 relative of the oracle's (or lower) and |d fs| <= 1 mm for most cells.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL_FIXED = 1e-9
+
+
+@pytest.fixture(scope="module")
+def handle(small_day):
+    import optimalinterpolation_b200 as oi
+    h = oi.Handle(0)
+    d = small_day
+    h.set_observations(d.x_train, d.y_train, d.t_train, d.z)
+    h.set_cells(d.X)
+    h.gather_neighbours(d.radius_km * 1000.0)
+    yield h
+    h.close()
+
+
+def test_neighbour_sets_bit_exact(handle, small_day, small_oracle):
+    offsets, indices = handle.get_neighbours()
+    o = small_oracle
+    lists = o.tree.query_ball_point(small_day.X, r=o.radius_m)
+    for c in range(len(small_day.X)):
+        got = indices[offsets[c]:offsets[c + 1]]
+        assert np.array_equal(got, np.sort(np.asarray(lists[c], dtype=np.int64))), c
+
+
+def test_neighbour_lattice_ties():
+    """Full 25 km lattice, centre on a lattice point, r = 300 km: 441 points incl. 4 exact ties
+     -- the boundary is inclusive."""
+    import optimalinterpolation_b200 as oi
+    jj, ii = np.meshgrid(np.arange(40), np.arange(40))
+    x = 25000.0 * jj.ravel(); y = 25000.0 * ii.ravel()
+    h = oi.Handle(0)
+    h.set_observations(x, y, np.zeros_like(x), np.zeros_like(x))
+    h.set_cells(np.array([[25000.0 * 20, 25000.0 * 20], [25000.0 * 20 + 1.0, 25000.0 * 20]]))
+    counts = h.gather_neighbours(300000.0)
+    assert counts[0] == 441
+    cx = 25000.0 * 20 + 1.0           # shifted centre: three of the four ties drop out
+    assert counts[1] == np.count_nonzero((x - cx) ** 2 + (y - 25000.0 * 20) ** 2 <= 300000.0 ** 2) == 438
+    h.close()
+
+
+def test_neighbour_random_boundary(small_day):
+    """Randomised near-boundary set equality against scipy's cKDTree (off-lattice coordinates)."""
+    import optimalinterpolation_b200 as oi
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(3)
+    x = rng.uniform(0, 1e6, 5000); y = rng.uniform(0, 1e6, 5000)
+    X = rng.uniform(2e5, 8e5, (300, 2))
+    # put points (almost) exactly on the circle of the first cells
+    th = rng.uniform(0, 2 * np.pi, 200)
+    x[:200] = X[0, 0] + 150000.0 * np.cos(th); y[:200] = X[0, 1] + 150000.0 * np.sin(th)
+    h = oi.Handle(0)
+    h.set_observations(x, y, np.zeros_like(x), np.zeros_like(x)); h.set_cells(X)
+    h.gather_neighbours(150000.0)
+    offsets, indices = h.get_neighbours()
+    lists = cKDTree(np.c_[x, y]).query_ball_point(X, r=150000.0)
+    for c in range(len(X)):
+        assert np.array_equal(indices[offsets[c]:offsets[c + 1]], np.sort(np.asarray(lists[c], dtype=np.int64)))
+    h.close()
+
+
+HYPER_SETS = {
+    "x0": lambda d: d.x0,
+    "notebook_optimum": lambda d: np.log([2.15e5, 1.40e5, 21.0, 0.0279, 0.00346, 0.1]),
+    "flat_large_ell": lambda d: np.log([2.0e6, 3.0e6, 60.0, 0.5, 0.02, 0.1]),
+    "short_ell": lambda d: np.log([4.0e4, 3.0e4, 2.0, 0.01, 0.002, 0.1]),
+}
+
+
+@pytest.mark.parametrize("name", list(HYPER_SETS))
+def test_nlml_grad_fixed_hypers(handle, small_day, small_oracle, name):
+    from oracle.gpr_oracle import nlml_grad
+    d, o = small_day, small_oracle
+    hyp = np.asarray(HYPER_SETS[name](d), dtype=float)
+    nlz, grad = handle.nlml_grad(hyp, d.mean)
+    cells = list(range(0, len(d.X), 7))
+    worst_f = worst_g = 0.0
+    for c in cells:
+        _, inp, out, _ = o.cell_data(c, sort=True)
+        f, g = nlml_grad(hyp, inp, out, np.ones(len(out)) * d.mean)
+        worst_f = max(worst_f, abs(nlz[c] - f) / abs(f))
+        gs = np.abs(g[:5]).max()
+        worst_g = max(worst_g, np.abs(grad[c, :5] - g[:5]).max() / gs)
+        assert grad[c, 5] == 0.0
+    print(f"{name}: worst rel nlZ {worst_f:.2e}, worst rel grad {worst_g:.2e} over {len(cells)} cells")
+    assert worst_f < RTOL_FIXED and worst_g < RTOL_FIXED
+
+
+def test_nlml_grad_exact_convention(handle, small_day):
+    hyp = np.log([2.15e5, 1.40e5, 21.0, 0.0279, 0.00346])
+    f0, g0 = handle.nlml_grad(hyp, small_day.mean, grad_convention=0)
+    f1, g1 = handle.nlml_grad(hyp, small_day.mean, grad_convention=1)
+    assert np.array_equal(f0, f1)
+    assert np.allclose(g1[:, 3:5] * 2, g0[:, 3:5], rtol=1e-15) and np.array_equal(g0[:, :3], g1[:, :3])
+    # the EXACT convention is the true derivative: central finite differences on a few cells
+    eps = 1e-5
+    for k in range(5):
+        hp, hm = hyp.copy(), hyp.copy(); hp[k] += eps; hm[k] -= eps
+        fp, _ = handle.nlml_grad(hp, small_day.mean); fm, _ = handle.nlml_grad(hm, small_day.mean)
+        fd = (fp - fm) / (2 * eps)
+        sel = slice(0, None, 50)
+        assert np.allclose(fd[sel], g1[sel, k], rtol=2e-5, atol=1e-5), k
+
+
+def test_predict_fixed_hypers(handle, small_day, small_oracle):
+    d, o = small_day, small_oracle
+    nc = len(d.X)
+    rng = np.random.default_rng(1)
+    hyp = np.tile([2.15e5, 1.40e5, 21.0, 0.0279, 0.00346], (nc, 1)) * rng.uniform(0.5, 2.0, (nc, 5))
+    p = handle.make_params(d.radius_km * 1000, d.T_mid, d.mean, d.x0, mode=1)
+    handle.run(p, hyp)
+    res = handle.get_results()
+    worst = np.zeros(3)
+    for c in range(0, nc, 5):
+        ref = o.gpr3d(c, hypers=hyp[c], sort=True)
+        got = res["out"][c]
+        for q in range(3):
+            worst[q] = max(worst[q], abs(got[q] - ref[q]) / abs(ref[q]))
+        assert np.array_equal(got[3:], hyp[c])
+    print("predict worst rel (fs, sfs2, lZ):", worst)
+    assert (worst < RTOL_FIXED).all()
+
+
+def test_cholesky_failure_semantics(small_day):
+    """Duplicated points with vanishing noise: K is singular -> NaN tuple for that cell, inf NLML."""
+    import optimalinterpolation_b200 as oi
+    x = np.array([0.0, 0.0, 25000.0, 25000.0, 50000.0]); y = np.zeros(5); t = np.array([1.0, 1.0, 2.0, 2.0, 3.0])
+    z = np.array([0.1, 0.1, 0.2, 0.2, 0.3])
+    h = oi.Handle(0)
+    h.set_observations(x, y, t, z); h.set_cells(np.array([[25000.0, 0.0], [9e6, 9e6]]))
+    counts = h.gather_neighbours(1e5)
+    assert list(counts) == [5, 0]
+    hyp = np.log([25000.0, 25000.0, 1.0, 1.0, 1e-300])
+    f, g = h.nlml_grad(hyp, 0.1)
+    assert np.isinf(f[0]) and np.isinf(g[0]).all() and np.isnan(f[1])
+    p = h.make_params(1e5, 2.0, 0.1, None, mode=1)
+    h.run(p, np.tile(np.exp(hyp), (2, 1)))
+    res = h.get_results()
+    assert np.isnan(res["out"]).all() and list(res["status"]) == [3, 4]
+    h.close()
+
+
+def test_fit_matches_oracle(small_day, small_oracle):
+    """Fitted path: device lockstep scipy-CG vs scipy.optimize.minimize(CG) on the oracle objective."""
+    import optimalinterpolation_b200 as oi
+    d, o = small_day, small_oracle
+    cells = np.arange(0, len(d.X), 12)
+    g = oi.GPRDay(d.x_train, d.y_train, d.t_train, d.z, d.X[cells], d.radius_km, d.mean, d.T_mid, d.x0)
+    res = g.run(opt=True)
+    out = res["out"]
+    dfs, ok_nl, both_nan = [], [], 0
+    for k, c in enumerate(cells):
+        ref, r = o.gpr3d(int(c), sort=True, return_result=True)
+        if np.isnan(ref[0]) or np.isnan(out[k, 0]):
+            # scipy ended on a NaN iterate (status 3): the reference returns the NaN tuple, so must we
+            both_nan += int(np.isnan(ref[0]) and np.isnan(out[k, 0]))
+            dfs.append(0.0 if (np.isnan(ref[0]) and np.isnan(out[k, 0])) else np.inf)
+            ok_nl.append(np.isnan(ref[0]) and np.isnan(out[k, 0]))
+            continue
+        dfs.append(abs(out[k, 0] - ref[0]) * 1000.0)
+        rel = (out[k, 2] - ref[2]) / abs(ref[2])      # lZ = -NLML: higher is better
+        ok_nl.append(rel > -1e-6)
+    dfs = np.array(dfs)
+    print(f"fit parity over {len(cells)} cells: |dfs| mm median {np.median(dfs):.3e} max {dfs.max():.3e}; "
+          f"frac <=1mm {np.mean(dfs <= 1.0):.3f}; NLML-ok frac {np.mean(ok_nl):.3f}; both-NaN {both_nan}; "
+          f"nfev mean {res['nfev'].mean():.1f}")
+    # the reference's stopping point is not invariant to 1e-16 perturbations, so a
+    # small tail of cells may land elsewhere; on this 52-cell sample allow 3 of them
+    assert np.mean(dfs <= 1.0) >= 0.94
+    assert np.mean(ok_nl) >= 0.90
