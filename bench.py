@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- GP cells/sec (fit + predict) on the synthetic 25 km pan-Arctic day (BASELINE.json).
+
+A step = one pass of the hot path (neighbour gather -> lockstep CG fit -> posterior) over one batch
+of cells: ``--gpus N`` stripes of the day (stripe s = every 8th ice cell starting at s, so each
+stripe has the day's n-histogram; ~2390 cells per stripe, per-GPU work fixed => weak scaling;
+at N=8 one step is the whole day).  Cells of a step are sharded over ranks by LPT on n^3
+(optimalinterpolation_b200/shard.py); the only collective is the final gather of the result rows.
+
+  value : cells/s with observations + cell coordinates already resident in HBM (timed: gather +
+          fit + predict + result gather), CUDA events on the launching stream, max over ranks
+  e2e   : the same through the single C-ABI call oi_gpr_day with pinned HOST buffers
+          (H2D of the inputs and D2H of the results inside the timed region)
+  --impl reference : the reference's CPU path (oracle port, see oracle/) on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "GP cells/sec (fit+predict), 25km Arctic day"
+N_STRIPES = 8
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--stripes-per-gpu", type=int, default=1)
+    ap.add_argument("--max-active", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frac", type=float, default=0.2, help="cheapest fraction of cells the CPU sample is drawn from")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([v.strip() for v in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def step_cells(day, n_stripes_in_step):
+    nc = len(day.X)
+    return np.sort(np.concatenate([np.arange(s, nc, N_STRIPES) for s in range(min(n_stripes_in_step, N_STRIPES))]))
+
+
+def reference_arm(args, rank, world):
+    """The reference's CPU implementation of the path (oracle port) on the host cores."""
+    if rank != 0:
+        return
+    import warnings
+    warnings.simplefilter("ignore")
+    from optimalinterpolation_b200.synthetic import make_day
+    from oracle import cpu_baseline
+    from scipy.spatial import cKDTree
+    day = make_day()
+    cells = step_cells(day, args.gpus * args.stripes_per_gpu)
+    counts = np.asarray(cKDTree(np.c_[day.x_train, day.y_train]).query_ball_point(
+        day.X, r=day.radius_km * 1000.0, return_length=True))
+    cores = os.cpu_count() or 1
+    vals, wall = [], []
+    for s in range(args.warmup + args.steps):
+        # warm-up steps use a much cheaper sample (processes/BLAS spin-up only)
+        frac = 0.02 if s < args.warmup else args.cpu_frac * 0.5
+        r = cpu_baseline.run_sample(day, counts, cells, cores=cores, frac=frac)
+        if s >= args.warmup:
+            vals.append(r["value"]); wall.append(r["wall_s"]); last = r
+    v = float(np.mean(vals))
+    sample = (f"{last['n_sample']} cells per step evenly from the cheapest {args.cpu_frac * 0.5:.0%} of the step's "
+              f"{len(cells)} cells (n {last['n_min']}..{last['n_max']}), one process per core, 1 BLAS thread each; "
+              f"cells/s scaled by the n^3 cost ratio {last['cost_ratio']:.4f} to the step's cost mix")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "cells/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(wall)) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.gpus * args.stripes_per_gpu}/8 stripes of the synthetic 25 km pan-Arctic day "
+                               f"({len(cells)} cells); CPU arm times a bounded sample per step"},
+        "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+    import optimalinterpolation_b200 as oi
+    from optimalinterpolation_b200.synthetic import make_day
+    from optimalinterpolation_b200.shard import lpt_partition, gather_results, imbalance
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    day = make_day()
+    cells = step_cells(day, world * args.stripes_per_gpu)
+    Xstep = day.X[cells]
+    h = oi.Handle(local_rank)
+    stream = torch.cuda.current_stream()
+    h.set_stream(stream.cuda_stream)
+
+    # pinned host staging of the inputs (e2e path copies from these every step)
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+        t.numpy()[...] = a
+        return t.numpy()
+    px, py, pt, pz = map(pinned, (day.x_train, day.y_train, day.t_train, day.z))
+
+    # planning (untimed, deterministic): counts of the step's cells -> LPT shard
+    h.set_observations(px, py, pt, pz)
+    h.set_cells(Xstep)
+    counts_step = h.gather_neighbours(day.radius_km * 1000.0).copy()
+    parts = lpt_partition(counts_step, world)
+    mine = parts[rank]
+    Xmine = pinned(Xstep[mine])
+    params = h.make_params(day.radius_km * 1000.0, day.T_mid, day.mean, day.x0, mode=0, max_active=args.max_active)
+
+    def step_resident():
+        h.gather_neighbours(day.radius_km * 1000.0)
+        h.run(params)
+        res = h.get_results()
+        st = h.stats()
+        full = gather_results(res["out"], mine, len(cells), parts)
+        return res, st, full
+
+    def step_e2e():
+        res = h.gpr_day(px, py, pt, pz, Xmine, params)
+        st = h.stats()
+        full = gather_results(res["out"], mine, len(cells), parts)
+        return res, st, full
+
+    # ---------------- device-resident arm ----------------
+    h.set_cells(Xmine)
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter(); e0.record(stream)
+    agg = {}
+    for _ in range(args.steps):
+        res, st, full = step_resident()
+        for k, v in st.items():
+            agg[k] = agg.get(k, 0) + v
+    e1.record(stream); barrier()
+    wall = time.perf_counter() - t0
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    tt = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
+    launches = torch.tensor([agg["n_launches"]], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    ms, wall_ms = float(tt[0]), float(tt[1])
+    value = len(cells) * args.steps / (ms * 1e-3)
+
+    # ---------------- end-to-end arm (host buffers through the one ABI call) ----------------
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter(); e0.record(stream)
+    for _ in range(args.steps):
+        res_e, st_e, full_e = step_e2e()
+    e1.record(stream); barrier()
+    tt = torch.tensor([e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_value = len(cells) * args.steps / (max(float(tt[0]), float(tt[1])) * 1e-3)
+    h2d = 4 * day.z.size * 8 + Xmine.size * 8
+    d2h = len(mine) * (64 + 12)
+    same = bool(np.array_equal(full, full_e, equal_nan=True))
+
+    if rank == 0:
+        # measured FP64 peak (MEASURED_PEAKS.json holds no FP64 entry): cuBLAS DGEMM 8192^3
+        a = torch.randn(8192, 8192, dtype=torch.float64, device=dev); b = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            a @ b
+        best = 1e9
+        for _ in range(4):
+            p0 = torch.cuda.Event(enable_timing=True); p1 = torch.cuda.Event(enable_timing=True)
+            p0.record(); a @ b; p1.record(); torch.cuda.synchronize(); best = min(best, p0.elapsed_time(p1))
+        peak_tf = 2 * 8192 ** 3 / best * 1e-9
+        del a, b
+        fam = {k: (agg["ms_" + k], agg["flops_" + k], agg["launches_" + k]) for k in ("chol", "trtri", "lauum")}
+        top = max(fam, key=lambda k: fam[k][0])
+        names = {"chol": "k_chol_update+k_chol_panel", "trtri": "k_trtri", "lauum": "k_lauum_trace"}
+        ach = fam[top][1] / fam[top][0] * 1e-9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top)
+        except Exception:
+            pass
+        roofline = {"bound": "tensor", "kernel": names[top], "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": ach / peak_tf, "traffic": traffic,
+                    "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry; "
+                                   "DMMA issue-rate microbenchmark: 37.1 TFLOP/s, profiles/r01_fp64_peak_microbench.txt)",
+                    "flops_per_launch": fam[top][1] / max(fam[top][2], 1), "ms_per_launch": fam[top][0] / max(fam[top][2], 1),
+                    "share_of_step": fam[top][0] / agg["ms_total"],
+                    "families": {names[k]: {"tflops": fam[k][1] / fam[k][0] * 1e-9, "ms": fam[k][0] / args.steps,
+                                            "share": fam[k][0] / agg["ms_total"]} for k in fam},
+                    "whole_step_tflops": agg["flops"] / (ms * 1e-3) * 1e-12 if world == 1 else None}
+        line = {
+            "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{world * args.stripes_per_gpu}/8 stripes of the synthetic 25 km pan-Arctic day "
+                                   f"(SURVEY.md 8d: 320x320 lattice, 19109 ice cells, 38144 obs, r=300 km, 9 days)",
+                       "cells_per_step": int(len(cells)), "n_obs": int(day.z.size),
+                       "n_min_median_max": [int(counts_step.min()), int(np.median(counts_step)), int(counts_step.max())],
+                       "optimiser": "scipy-CG restatement (reference gradient convention), x0 as GPR_CS2S3.py:217",
+                       "sharding": f"LPT on n^3 over {world} ranks, imbalance {imbalance(counts_step, parts):.4f}",
+                       "cache": "per-iteration working set (sum of n_pad^2*8 B over active cells, GBs) is far larger than the 126 MB L2; no L2 flush needed"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "identical_to_resident_arm": same},
+            "gpu_launches": int(launches.item()),
+            "wall_ms_per_step": wall_ms / args.steps,
+            "nfev_mean": float(res["nfev"].mean()), "evals_per_step": agg["n_evals"] / args.steps,
+            "iterations_per_step": agg["n_iterations"] / args.steps,
+            "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            import warnings
+            warnings.simplefilter("ignore")
+            from oracle import cpu_baseline
+            cores = os.cpu_count() or 1
+            cpu_baseline.run_sample(day, counts_full(day, h, cells, counts_step), cells, cores=cores, frac=0.02)
+            r = cpu_baseline.run_sample(day, counts_full(day, h, cells, counts_step), cells, cores=cores, frac=args.cpu_frac)
+            line["cpu_baseline"] = {
+                "value": r["value"], "unit": "cells/s", "cores": cores, "kind": "port",
+                "sample": (f"{r['n_sample']} cells evenly from the cheapest {args.cpu_frac:.0%} of the step's {len(cells)} cells "
+                           f"(n {r['n_min']}..{r['n_max']}), full scipy-CG fit + predict each, one process per core with 1 BLAS "
+                           f"thread, {r['wall_s']:.1f} s wall; raw {r['raw_cells_per_s']:.4f} cells/s scaled by the n^3 cost "
+                           f"ratio {r['cost_ratio']:.4f} to the step's cost mix")}
+        print(json.dumps(line))
+    h.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def counts_full(day, h, cells, counts_step):
+    """neighbour counts indexed by the day's cell index (only the step's cells are filled)."""
+    c = np.zeros(len(day.X), dtype=np.int64)
+    c[cells] = counts_step
+    return c
+
+
+if __name__ == "__main__":
+    main()

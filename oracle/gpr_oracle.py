@@ -90,8 +90,8 @@ def neighbours_brute(x_train, y_train, centre_xy, radius_m):
 
 
 def predict(inputs, outputs, mean, Xs, ell, sf2, sn2):
-    """Posterior at one target, GPR_CS2S3.py:173-191.  Returns (fs, sfs2 [std-dev], lZ)
-    or three NaNs on Cholesky failure."""
+    """Posterior at one target, GPR_CS2S3.py:173-191.  Returns (fs, sfs2 [std-dev], lZ), or None
+    when np.linalg raises LinAlgError (the reference then returns its NaN tuple, :187-191)."""
     n = len(outputs)
     mX = np.ones(n) * mean
     Kx = matern32(inputs, ell, sf2)
@@ -99,14 +99,14 @@ def predict(inputs, outputs, mean, Xs, ell, sf2, sn2):
     Kxs = matern32(Xs, ell, sf2)
     try:
         L = np.linalg.cholesky(Kx + np.eye(n) * sn2)
+        A = np.linalg.solve(L.T, np.linalg.solve(L, (outputs - mX)))
+        lZ = -np.dot((outputs - mX).T, A) / 2 - np.log(L.diagonal()).sum() - n * _LOG2PI / 2
+        v = np.linalg.solve(L, Kxsx)
+        fs = mean + np.dot(Kxsx.T, A)
+        with np.errstate(invalid='ignore'):
+            sfs2 = np.sqrt((Kxs - np.dot(v.T, v)).diagonal())
     except np.linalg.LinAlgError:
-        return np.nan, np.nan, np.nan
-    A = np.linalg.solve(L.T, np.linalg.solve(L, (outputs - mX)))
-    lZ = -np.dot((outputs - mX).T, A) / 2 - np.log(L.diagonal()).sum() - n * _LOG2PI / 2
-    v = np.linalg.solve(L, Kxsx)
-    fs = mean + np.dot(Kxsx.T, A)
-    with np.errstate(invalid='ignore'):
-        sfs2 = np.sqrt((Kxs - np.dot(v.T, v)).diagonal())
+        return None
     return float(fs[0]), float(sfs2[0]), float(lZ)
 
 
@@ -151,9 +151,9 @@ class DayOracle:
             h, res = fit(inputs, outputs, self.mean, self.x0, return_result=True)
         else:
             h = np.asarray(hypers, dtype=float)
-        fs, sfs2, lZ = predict(inputs, outputs, self.mean, Xs, [h[0], h[1], h[2]], h[3], h[4])
-        if np.isnan(lZ):
+        p = predict(inputs, outputs, self.mean, Xs, [h[0], h[1], h[2]], h[3], h[4])
+        if p is None:
             out = (np.nan,) * 8
         else:
-            out = (fs, sfs2, lZ, h[0], h[1], h[2], h[3], h[4])
+            out = (p[0], p[1], p[2], h[0], h[1], h[2], h[3], h[4])
         return (out, res) if return_result else out

@@ -1,0 +1,111 @@
+"""CPU: the oracle (numpy restatement) against (a) the golden vectors produced by the reference's
+own functions and (b) those functions themselves when /root/reference is present."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.npz")
+HYPERS = {
+    "x0": None,
+    "notebook_optimum": np.log([2.15e5, 1.40e5, 21.0, 0.0279, 0.00346, 0.1]),
+    "flat_large_ell": np.log([2.0e6, 3.0e6, 60.0, 0.5, 0.02, 0.1]),
+}
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def _same_libs(gold):
+    import scipy
+    return str(gold["numpy"]) == np.__version__ and str(gold["scipy"]) == scipy.__version__
+
+
+def test_neighbours_match_golden(gold, small_day, small_oracle):
+    from oracle.gpr_oracle import neighbours_brute
+    for c in gold["cells"]:
+        ID, *_ = small_oracle.cell_data(int(c), sort=True)
+        assert np.array_equal(np.array(ID), gold[f"nbr_{c}"])
+        assert np.array_equal(neighbours_brute(small_day.x_train, small_day.y_train, small_day.X[c], small_oracle.radius_m),
+                              gold[f"nbr_{c}"])
+
+
+def test_smlii_matches_golden(gold, small_day, small_oracle):
+    from oracle.gpr_oracle import nlml_grad
+    for c in gold["cells"]:
+        _, inp, out, _ = small_oracle.cell_data(int(c))
+        for name, h in HYPERS.items():
+            h = np.array(small_day.x0 if h is None else h, dtype=float)
+            f, g = nlml_grad(h, inp, out, np.ones(len(out)) * small_day.mean)
+            ref = gold[f"smlii_{c}_{name}"]
+            if _same_libs(gold):
+                assert f == ref[0] and np.array_equal(g, ref[1:]), (c, name)
+            else:
+                assert np.allclose(np.r_[f, g], ref, rtol=1e-10, atol=1e-12)
+            assert g[5] == 0.0          # dead sixth variable (GPR_CS2S3.py:217, :131)
+
+
+def test_kernel_matches_golden(gold, small_day, small_oracle):
+    from oracle.gpr_oracle import matern32
+    c = int(gold["cells"][1])
+    _, inp, _, _ = small_oracle.cell_data(c)
+    for name, h in HYPERS.items():
+        h = np.array(small_day.x0 if h is None else h, dtype=float)
+        K, dK = matern32(inp, np.exp(h[:3]), np.exp(h[3]), want_grad=True)
+        assert np.allclose(K[:12, :12], gold[f"kernel_{name}_K"], rtol=1e-13, atol=0)
+        assert np.allclose(dK[:, :12, :12], gold[f"kernel_{name}_dK"], rtol=1e-13, atol=1e-300)
+        assert np.allclose([K.sum(), dK[0].sum(), dK[1].sum(), dK[2].sum()], gold[f"kernel_{name}_sums"], rtol=1e-12)
+        assert np.allclose(np.diag(K), np.exp(h[3]))
+
+
+def test_gpr3d_fixed_matches_golden(gold, small_oracle):
+    for c in gold["cells"]:
+        got = small_oracle.gpr3d(int(c), hypers=[2.15e5, 1.40e5, 21.0, 0.0279, 0.00346])
+        assert np.allclose(got[:2], gold[f"gpr3d_fixed_{c}"], rtol=1e-11, equal_nan=True)
+
+
+@pytest.mark.parametrize("k", range(4))
+def test_gpr3d_fit_matches_golden(gold, small_oracle, k):
+    import warnings
+    warnings.simplefilter("ignore")
+    c = int(gold["fit_cells"][k])
+    got = np.array(small_oracle.gpr3d(c), dtype=float)
+    ref = gold[f"gpr3d_{c}"]
+    if _same_libs(gold):
+        assert np.array_equal(got, ref, equal_nan=True)
+    else:
+        assert np.allclose(got[:3], ref[:3], rtol=1e-5, equal_nan=True)
+
+
+def test_oracle_equals_reference_functions(small_day, small_oracle):
+    """Where the reference is mounted, run its functions verbatim and demand bit-identity."""
+    from oracle import reference_functions as rf
+    if not rf.available():
+        pytest.skip("/root/reference not present (GPU box): golden vectors cover this")
+    import warnings
+    warnings.simplefilter("ignore")
+    from oracle.gpr_oracle import nlml_grad, matern32
+    ns = rf.day_namespace(small_day)
+    for c in (17, 333):
+        _, inp, out, Xs = small_oracle.cell_data(c)
+        mX = np.ones(len(out)) * small_day.mean
+        for h in (np.array(small_day.x0), np.log([2.15e5, 1.40e5, 21.0, 0.0279, 0.00346, 0.1])):
+            f0, g0 = ns["SMLII"](h, inp, out, mX)
+            f1, g1 = nlml_grad(h, inp, out, mX)
+            assert float(np.asarray(f0).reshape(-1)[0]) == f1 and np.array_equal(g0, g1)
+            ell = list(np.exp(h[:3]))
+            assert np.array_equal(ns["SGPkernel"](inp, xs=Xs, ell=ell, sigma=np.exp(h[3])), matern32(inp, ell, np.exp(h[3]), xs=Xs))
+    assert np.array_equal(np.array(ns["GPR3D"](333)), np.array(small_oracle.gpr3d(333)), equal_nan=True)
+
+
+def test_cholesky_failure_semantics():
+    """Singular K: (inf, inf-vector) from SMLII, NaN tuple from GPR3D (GPR_CS2S3.py:139-140, :187-189)."""
+    from oracle.gpr_oracle import nlml_grad, predict
+    x = np.array([[0.0, 0.0, 1.0], [0.0, 0.0, 1.0], [25000.0, 0.0, 2.0]])
+    y = np.array([0.1, 0.1, 0.2])
+    h = np.log([25000.0, 25000.0, 1.0, 1.0, 1e-300, 0.1])
+    f, g = nlml_grad(h, x, y, np.ones(3) * 0.1)
+    assert np.isinf(f) and np.isinf(g).all()
+    assert predict(x, y, 0.1, np.array([[0.0, 0.0, 1.0]]), [25000.0, 25000.0, 1.0], 1.0, 1e-300) is None
