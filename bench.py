@@ -2,9 +2,9 @@
 """bench.py -- GP cells/sec (fit + predict) on the synthetic 25 km pan-Arctic day (BASELINE.json).
 
 A step = one pass of the hot path (neighbour gather -> lockstep CG fit -> posterior) over one batch
-of cells: ``--gpus N`` stripes of the day (stripe s = every 8th ice cell starting at s, so each
-stripe has the day's n-histogram; ~2390 cells per stripe, per-GPU work fixed => weak scaling;
-at N=8 one step is the whole day).  Cells of a step are sharded over ranks by LPT on n^3
+of cells: ``--gpus N`` stripes of the day (stripe s = every 16th ice cell starting at s, so each
+stripe has the day's n-histogram; ~1195 cells per stripe, per-GPU work fixed => weak scaling;
+at N=8 one step is half the day).  Cells of a step are sharded over ranks by LPT on n^3
 (optimalinterpolation_b200/shard.py); the only collective is the final gather of the result rows.
 
   value : cells/s with observations + cell coordinates already resident in HBM (timed: gather +
@@ -27,7 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "GP cells/sec (fit+predict), 25km Arctic day"
-N_STRIPES = 8
+N_STRIPES = 16
 
 
 def parse():
@@ -106,7 +106,7 @@ def reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "cells/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(wall)) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.gpus * args.stripes_per_gpu}/8 stripes of the synthetic 25 km pan-Arctic day "
+        "config": {"workload": f"{args.gpus * args.stripes_per_gpu}/16 stripes of the synthetic 25 km pan-Arctic day "
                                f"({len(cells)} cells); CPU arm times a bounded sample per step"},
         "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -245,7 +245,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{world * args.stripes_per_gpu}/8 stripes of the synthetic 25 km pan-Arctic day "
+            "config": {"workload": f"{world * args.stripes_per_gpu}/16 stripes of the synthetic 25 km pan-Arctic day "
                                    f"(SURVEY.md 8d: 320x320 lattice, 19109 ice cells, 38144 obs, r=300 km, 9 days)",
                        "cells_per_step": int(len(cells)), "n_obs": int(day.z.size),
                        "n_min_median_max": [int(counts_step.min()), int(np.median(counts_step)), int(counts_step.max())],

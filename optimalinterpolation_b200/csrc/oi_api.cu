@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "../../include/oi_b200.h"
@@ -257,7 +258,13 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
     if (rcode) return rcode;
 
     OiPacked pk{h->px, h->py, h->pt, h->pr};
-    std::vector<int> active;
+    // OI_TRACE=<file>: one CSV line per lockstep iteration (active cells, Nmax, ms per kernel family)
+    FILE* trace = nullptr;
+    if (const char* tp = std::getenv("OI_TRACE")) {
+        trace = std::fopen(tp, "a");
+        if (trace) std::fprintf(trace, "iter,active,Nmax,ms_build,ms_chol,ms_fwd,ms_trtri,ms_alpha,ms_lauum,ms_finalize,flops_factor\n");
+    }
+    std::vector<int> active, cnt_gt;
     size_t used = 0, next = 0;
     double ms_factor = 0;
     while (true) {
@@ -285,7 +292,7 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
             s.part = (double*)(h->arena + off); off += align_up((size_t)(N + 8 + 5 * N * (N + 1) / 2) * 8, 256);
             s.fail = h->d_fail + a;
             s.pt_off = 0;   // filled below from the CSR offsets
-            s.cell = c; s.n = n; s.npad = npad; s.N = N;
+            s.cell = c; s.n = n; s.npad = npad; s.N = N; s.n16 = (n + 15) / 16 * 16; s.pad_ = 0;
             Nmax = std::max(Nmax, N);
             double dn = n;
             flf_chol += dn * dn * dn / 3;
@@ -293,22 +300,29 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
             else { fl += dn * dn * dn + 22 * dn * dn; flf += dn * dn * dn; flf_fit += dn * dn * dn; nev++; }
         }
         for (int a = 0; a < A; a++) h->h_slots[a].pt_off = h->h_offsets[active[a]];
+        // cnt_gt[x] = number of (size-sorted) slots with more than x blocks
+        cnt_gt.assign((size_t)Nmax + 2, 0);
+        for (int a = 0; a < A; a++) cnt_gt[h->h_slots[a].N]++;              // histogram of N
+        for (int x = Nmax; x >= 0; x--) cnt_gt[x] = cnt_gt[x + 1] + cnt_gt[x];  // -> #slots with N >= x
+        for (int x = 0; x <= Nmax; x++) cnt_gt[x] = cnt_gt[x + 1];             // -> #slots with N > x
+        const int* cg = cnt_gt.data();
         CK(cudaMemcpyAsync(h->d_slots, h->h_slots, (size_t)A * sizeof(OiSlot), cudaMemcpyHostToDevice, h->st));
         CK(cudaEventRecord(h->ev[0], h->st));
-        oi_launch_build(h->d_slots, A, Nmax, h->ca, pk, h->st);
+        oi_launch_build(h->d_slots, A, Nmax, cg, h->ca, pk, h->st);
         CK(cudaEventRecord(h->ev[1], h->st));
         for (int k = 0; k < Nmax; k++) {
-            oi_launch_chol_update(h->d_slots, A, Nmax, k, h->st);
-            oi_launch_chol_panel(h->d_slots, A, Nmax, k, h->st);
+            oi_launch_chol_update(h->d_slots, A, Nmax, cg, k, h->st);
+            oi_launch_chol_panel(h->d_slots, A, Nmax, cg, k, h->st);
         }
+        oi_launch_scale_rows(h->d_slots, A, Nmax, cg, h->st);
         CK(cudaEventRecord(h->ev[2], h->st));
         oi_launch_fwd(h->d_slots, A, h->ca, pk, t_pred, h->st);
         CK(cudaEventRecord(h->ev[3], h->st));
-        for (int d = 1; d < Nmax; d++) oi_launch_trtri(h->d_slots, A, Nmax, d, h->ca.phase, h->st);
+        for (int d = 1; d < Nmax; d++) oi_launch_trtri(h->d_slots, A, Nmax, cg, d, h->ca.phase, h->st);
         CK(cudaEventRecord(h->ev[4], h->st));
         oi_launch_alpha(h->d_slots, A, Nmax, h->ca.phase, h->st);
         CK(cudaEventRecord(h->ev[5], h->st));
-        oi_launch_lauum_trace(h->d_slots, A, Nmax, h->ca, pk, h->st);
+        oi_launch_lauum_trace(h->d_slots, A, Nmax, cg, h->ca, pk, h->st);
         CK(cudaEventRecord(h->ev[6], h->st));
         oi_launch_finalize(h->d_slots, A, h->ca, rc, h->d_slot_phase, h->st);
         CK(cudaEventRecord(h->ev[7], h->st));
@@ -320,11 +334,13 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
         h->stats.ms_build += m[0]; h->stats.ms_chol += m[1]; h->stats.ms_fwd += m[2]; h->stats.ms_trtri += m[3];
         h->stats.ms_alpha += m[4]; h->stats.ms_lauum += m[5]; h->stats.ms_finalize += m[6];
         ms_factor += m[1] + m[3] + m[5];
+        if (trace) std::fprintf(trace, "%lld,%d,%d,%.4f,%.4f,%.4f,%.4f,%.4f,%.4f,%.4f,%.6g\n", (long long)h->stats.n_iterations, A, Nmax,
+                                m[0], m[1], m[2], m[3], m[4], m[5], m[6], flf);
         h->stats.flops += fl; h->stats.flops_factor += flf; h->stats.n_evals += nev;
         h->stats.flops_chol += flf_chol; h->stats.flops_trtri += flf_fit / 3; h->stats.flops_lauum += flf_fit / 3;
-        h->stats.launches_chol += 2 * Nmax - 1; h->stats.launches_trtri += std::max(0, Nmax - 1); h->stats.launches_lauum += 1;
+        h->stats.launches_chol += 2 * Nmax; h->stats.launches_trtri += std::max(0, Nmax - 1); h->stats.launches_lauum += 1;
         h->stats.n_iterations++;
-        h->stats.n_launches += 1 + Nmax + std::max(0, Nmax - 1) + 1 + std::max(0, Nmax - 1) + 2 + 1;
+        h->stats.n_launches += 1 + Nmax + std::max(0, Nmax - 1) + (Nmax > 1) + 1 + std::max(0, Nmax - 1) + 2 + 1;
         // retire finished cells, keep the rest in (descending n) order
         size_t w = 0;
         for (int a = 0; a < A; a++) {
@@ -336,6 +352,7 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
         active.resize(w);
     }
     h->stats.ms_factor += ms_factor;
+    if (trace) std::fclose(trace);
     return OI_OK;
 }
 

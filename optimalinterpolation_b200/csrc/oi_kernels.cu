@@ -27,6 +27,11 @@
 #define PIPE_BYTES (STAGES * STAGE_DOUBLES * 8)
 
 #define ROOT3 1.7320508075688772   // np.sqrt(3.)
+#ifdef OI_EXP_SAMEBLOCK
+#define OI_FAILED(s) false
+#else
+#define OI_FAILED(s) (*(volatile int*)(s).fail != 0)
+#endif
 
 // ------------------------------------------------------------------------------------------
 // small helpers
@@ -133,12 +138,13 @@ __global__ void k_pack(const int* __restrict__ indices, long long total, const d
 // kernel (2): covariance tiles.  K = sf2*(1+Q)exp(-Q) + sn2*I on the lower block triangle
 // (GPR_CS2S3.py:93-94, :126); padding rows/cols are identity so every later tile is full.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_build(const OiSlot* __restrict__ slots, OiCellArrays ca, OiPacked pk) {
+__global__ void __launch_bounds__(256) k_build(const OiSlot* __restrict__ slots, OiCellArrays ca, OiPacked pk, int row) {
     const OiSlot s = slots[blockIdx.y];
     int i, j;
-    tile_ij(blockIdx.x, i, j);
+    if (row >= 0) { i = row; j = blockIdx.x; }      // one launch per block row (exact grids for big batches)
+    else tile_ij(blockIdx.x, i, j);
     if (i >= s.N) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *s.fail = 0;
+    if (i == 0 && threadIdx.x == 0) *s.fail = 0;
     __shared__ double ru[3][NB], cu[3][NB];
     const double* h = ca.hyp + 5 * (size_t)s.cell;
     const double sf2 = h[3], sn2 = h[4];
@@ -186,30 +192,64 @@ __device__ __forceinline__ void load_stage(double* st, const double* __restrict_
     for (int it = 0; it < 4; it++) {
         int c = tid + it * GEMM_THREADS;      // 0..511
         int row = c >> 3, col = (c & 7) * 2;
+#ifdef OI_EXP_SAMEBLOCK
+        // experiment: every chunk re-reads the first chunk of the panel (L1/L2 resident) -> compute-only bound
+        cp_async16(&As[row * LDS_ + col], &A[(long long)row * lda + (kk & 0) + col]);
+        cp_async16(&Bs[row * LDS_ + col], &B[(long long)row * ldb + (kk & 0) + col]);
+#else
         cp_async16(&As[row * LDS_ + col], &A[(long long)row * lda + kk + col]);
         cp_async16(&Bs[row * LDS_ + col], &B[(long long)row * ldb + kk + col]);
+#endif
     }
 }
 
-__device__ __forceinline__ void mma_chunk(double (&acc)[4][4][2], const double* As, const double* Bs, int lda_s, int ldb_s,
-                                          int wm, int wn, int lane, int ksteps) {
+// Sub-tile ranges: a warp computes the 8x8 sub-tiles mb in [mlo, mhi) x nb in [nlo, nhi) of its 32x32
+// warp tile for one K chunk.  All bounds are in {0, 2, 4} (structure comes in multiples of 16), so each
+// combination is its own fully unrolled code path; ranges are warp-uniform.  They skip structural zeros
+// (triangular diagonal blocks), the unused half of diagonal tiles and the rows/cols beyond the cell's real
+// size in its last block.
+struct SubRange { int mlo, mhi, nlo, nhi; };
+__device__ __forceinline__ int clamp024(int v) { return v <= 0 ? 0 : (v >= 32 ? 4 : (v >= 16 ? 2 : 0)); }
+// sub-tiles whose first row (col) is < limit / whose last row (col) is >= limit, limit a multiple of 16
+__device__ __forceinline__ int hi_lt(int w, int limit) { return clamp024(limit - w * 32); }
+__device__ __forceinline__ int lo_ge(int w, int limit) { return clamp024(limit - w * 32); }
+#define SR_ALL SubRange{0, 4, 0, 4}
+
+template <int MLO, int MHI, int NLO, int NHI>
+__device__ __forceinline__ void mma_chunk_t(double (&acc)[4][4][2], const double* As, const double* Bs, int lda_s, int ldb_s,
+                                            int wm, int wn, int lane, int kofs, int ksteps) {
     const int fr = lane >> 2, fc = lane & 3;
+#pragma unroll
     for (int ks = 0; ks < ksteps; ks++) {
         double a[4], b[4];
 #pragma unroll
-        for (int mb = 0; mb < 4; mb++) a[mb] = As[(wm * 32 + mb * 8 + fr) * lda_s + ks * 4 + fc];
+        for (int mb = MLO; mb < MHI; mb++) a[mb] = As[(wm * 32 + mb * 8 + fr) * lda_s + kofs + ks * 4 + fc];
 #pragma unroll
-        for (int nb = 0; nb < 4; nb++) b[nb] = Bs[(wn * 32 + nb * 8 + fr) * ldb_s + ks * 4 + fc];
+        for (int nb = NLO; nb < NHI; nb++) b[nb] = Bs[(wn * 32 + nb * 8 + fr) * ldb_s + kofs + ks * 4 + fc];
 #pragma unroll
-        for (int mb = 0; mb < 4; mb++)
+        for (int mb = MLO; mb < MHI; mb++)
 #pragma unroll
-            for (int nb = 0; nb < 4; nb++) dmma(acc[mb][nb], a[mb], b[nb]);
+            for (int nb = NLO; nb < NHI; nb++) dmma(acc[mb][nb], a[mb], b[nb]);
     }
 }
+template <int MLO, int MHI>
+__device__ __forceinline__ void mma_chunk_n(double (&acc)[4][4][2], const double* As, const double* Bs, int lda_s, int ldb_s,
+                                            int wm, int wn, int lane, int kofs, int ksteps, int nlo, int nhi) {
+    if (nlo == 0 && nhi == 4) mma_chunk_t<MLO, MHI, 0, 4>(acc, As, Bs, lda_s, ldb_s, wm, wn, lane, kofs, ksteps);
+    else if (nlo == 0 && nhi == 2) mma_chunk_t<MLO, MHI, 0, 2>(acc, As, Bs, lda_s, ldb_s, wm, wn, lane, kofs, ksteps);
+    else if (nlo == 2 && nhi == 4) mma_chunk_t<MLO, MHI, 2, 4>(acc, As, Bs, lda_s, ldb_s, wm, wn, lane, kofs, ksteps);
+}
+__device__ __forceinline__ void mma_chunk(double (&acc)[4][4][2], const double* As, const double* Bs, int lda_s, int ldb_s,
+                                          int wm, int wn, int lane, int kofs, int ksteps, SubRange r) {
+    if (r.mlo == 0 && r.mhi == 4) mma_chunk_n<0, 4>(acc, As, Bs, lda_s, ldb_s, wm, wn, lane, kofs, ksteps, r.nlo, r.nhi);
+    else if (r.mlo == 0 && r.mhi == 2) mma_chunk_n<0, 2>(acc, As, Bs, lda_s, ldb_s, wm, wn, lane, kofs, ksteps, r.nlo, r.nhi);
+    else if (r.mlo == 2 && r.mhi == 4) mma_chunk_n<2, 4>(acc, As, Bs, lda_s, ldb_s, wm, wn, lane, kofs, ksteps, r.nlo, r.nhi);
+}
 
+template <class MaskFn>
 __device__ __forceinline__ void gemm_nt_stream(double (&acc)[4][4][2], const double* __restrict__ A, long long lda,
                                                const double* __restrict__ B, long long ldb, int k0, int k1,
-                                               double* smem) {
+                                               double* smem, MaskFn maskfn) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wm = warp >> 1, wn = warp & 1;
     const int nk = (k1 - k0) / KT;
@@ -225,7 +265,7 @@ __device__ __forceinline__ void gemm_nt_stream(double (&acc)[4][4][2], const dou
         if (nx < nk) load_stage(smem + (nx % STAGES) * STAGE_DOUBLES, A, lda, B, ldb, k0 + nx * KT, tid);
         cp_async_commit();
         const double* st = smem + (it % STAGES) * STAGE_DOUBLES;
-        mma_chunk(acc, st, st + NB * LDS_, LDS_, LDS_, wm, wn, lane, KT / 4);
+        mma_chunk(acc, st, st + NB * LDS_, LDS_, LDS_, wm, wn, lane, 0, KT / 4, maskfn(k0 + it * KT));
     }
     cp_async_wait<0>();
     __syncthreads();
@@ -240,100 +280,199 @@ __device__ __forceinline__ void gemm_nt_stream(double (&acc)[4][4][2], const dou
 #define FRAG_COL(wn, nb, lane) ((wn) * 32 + (nb) * 8 + (((lane) & 3) << 1))
 
 // ------------------------------------------------------------------------------------------
+// 64x64 diagonal block: Cholesky factor (lower, in place in T) and its inverse (W), both in shared
+// memory, on 8x8 sub-blocks: the 8x8 pivot block is factored + inverted by one warp in registers
+// (dpotf2 order of operations; a pivot <= 0 sets *s_bad, a NaN pivot propagates -- OpenBLAS potf2
+// semantics, which is what np.linalg.cholesky runs), every other sub-block operation (panel solve,
+// trailing update, inverse by block distance) is one or two DMMA m8n8k4 per 8x8 block.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void diag_factor_invert(double* T, double* W, double* sc, int* s_bad, int tid) {
+    const int warp = tid >> 5, lane = tid & 31, fr = lane >> 2, fc = lane & 3;
+    for (int j = 0; j < 8; j++) {
+        const int jb = j * 8;
+        if (warp == 0) {
+            const int r = lane & 7;
+            double a[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) a[c] = T[(jb + r) * TS + jb + c];
+            bool bad = false;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+#pragma unroll
+                for (int l = 0; l < c; l++) {
+                    double acl = __shfl_sync(0xffffffffu, a[l], c, 8);      // L[c][l]
+                    if (r >= c) a[c] -= a[l] * acl;
+                }
+                double piv = __shfl_sync(0xffffffffu, a[c], c, 8);
+                if (piv <= 0.0) bad = true;
+                double sq = sqrt(piv), inv = 1.0 / sq;
+                if (r == c) a[c] = sq;
+                else if (r > c) a[c] *= inv;
+            }
+            if (bad) {
+                if (lane == 0) *s_bad = 1;
+            } else {
+                if (lane < 8) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) if (c <= r) T[(jb + r) * TS + jb + c] = a[c];
+                }
+                __syncwarp();
+                // X = L8^-1, lane b owns column b:  x[rr] = -(sum_{l<rr} L[rr][l] x[l]) / L[rr][rr]
+                const int b = r;
+                double x[8];
+#pragma unroll
+                for (int rr = 0; rr < 8; rr++) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int l = 0; l < rr; l++) sacc += T[(jb + rr) * TS + jb + l] * x[l];
+                    double dinv = 1.0 / T[(jb + rr) * TS + jb + rr];
+                    x[rr] = (rr < b) ? 0.0 : ((rr == b) ? dinv : -sacc * dinv);
+                }
+                if (lane < 8) {
+#pragma unroll
+                    for (int rr = 0; rr < 8; rr++) if (rr >= b) W[(jb + rr) * TS + jb + b] = x[rr];
+                }
+            }
+        }
+        __syncthreads();
+#ifndef OI_EXP_SAMEBLOCK
+        if (*s_bad) return;
+#endif
+        // panel: L_ij = A_ij * X_jj^T  (i > j)
+        for (int i = j + 1 + warp; i < 8; i += 4) {
+            double c2[2] = {0.0, 0.0};
+#pragma unroll
+            for (int ks = 0; ks < 2; ks++)
+                dmma(c2, T[(i * 8 + fr) * TS + jb + ks * 4 + fc], W[(jb + fr) * TS + jb + ks * 4 + fc]);
+            __syncwarp();
+            T[(i * 8 + fr) * TS + jb + fc * 2] = c2[0];
+            T[(i * 8 + fr) * TS + jb + fc * 2 + 1] = c2[1];
+        }
+        __syncthreads();
+        // trailing update: A_il -= L_ij L_lj^T  (j < l <= i)
+        const int m = 7 - j, cnt = m * (m + 1) / 2;
+        for (int q = warp; q < cnt; q += 4) {
+            int ii, ll;
+            tile_ij(q, ii, ll);
+            const int i = j + 1 + ii, l = j + 1 + ll;
+            double c2[2];
+            c2[0] = T[(i * 8 + fr) * TS + l * 8 + fc * 2];
+            c2[1] = T[(i * 8 + fr) * TS + l * 8 + fc * 2 + 1];
+#pragma unroll
+            for (int ks = 0; ks < 2; ks++)
+                dmma(c2, -T[(i * 8 + fr) * TS + jb + ks * 4 + fc], T[(l * 8 + fr) * TS + jb + ks * 4 + fc]);
+            T[(i * 8 + fr) * TS + l * 8 + fc * 2] = c2[0];
+            T[(i * 8 + fr) * TS + l * 8 + fc * 2 + 1] = c2[1];
+        }
+        __syncthreads();
+    }
+    // inverse by 8x8 block distance: W_ik = -X_ii * sum_{j=k}^{i-1} L_ij W_jk
+    for (int d = 1; d < 8; d++) {
+        for (int kb = warp; kb + d < 8; kb += 4) {
+            const int i = kb + d;
+            double c1[2] = {0.0, 0.0};
+            for (int jj = kb; jj < i; jj++) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ks++)
+                    dmma(c1, T[(i * 8 + fr) * TS + jj * 8 + ks * 4 + fc], W[(jj * 8 + ks * 4 + fc) * TS + kb * 8 + fr]);
+            }
+            sc[fr * 8 + fc * 2] = c1[0];
+            sc[fr * 8 + fc * 2 + 1] = c1[1];
+            __syncwarp();
+            double c2[2] = {0.0, 0.0};
+#pragma unroll
+            for (int ks = 0; ks < 2; ks++)
+                dmma(c2, W[(i * 8 + fr) * TS + i * 8 + ks * 4 + fc], sc[(ks * 4 + fc) * 8 + fr]);
+            W[(i * 8 + fr) * TS + kb * 8 + fc * 2] = -c2[0];
+            W[(i * 8 + fr) * TS + kb * 8 + fc * 2 + 1] = -c2[1];
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // kernel (3a): left-looking block-column update  A_ik -= sum_{j<k} L_ij L_kj^T  (i >= k);
 // the CTA of the diagonal tile then factors it in shared memory (dpotrf semantics: a pivot
 // <= 0 or NaN raises the cell's fail flag), inverts the 64x64 factor and stores
 //   Dinv[k] = L_kk^-1 (row-major)   and   M(k,k) = U_kk = L_kk^-T (upper, zeros below).
 // ------------------------------------------------------------------------------------------
-#define TD 65
 __global__ void __launch_bounds__(GEMM_THREADS) k_chol_update(const OiSlot* __restrict__ slots, int k) {
     extern __shared__ __align__(16) double smem[];
     const OiSlot s = slots[blockIdx.y];
     const int i = k + blockIdx.x;
     if (i >= s.N) return;
-    if (*(volatile int*)s.fail) return;
+    if (k == 0 && i != 0) return;          // nothing to subtract from the first block column
+    if (OI_FAILED(s)) return;
     const long long ld = s.npad;
     double acc[4][4][2];
     ACC_ZERO(acc);
-    gemm_nt_stream(acc, s.M + (long long)i * NB * ld, ld, s.M + (long long)k * NB * ld, ld, 0, k * NB, smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 1, wn = warp & 1;
+    // the tile being updated is fetched up front so its latency hides behind the K loop
+    double2 cin[4][4];
+    {
+        const double* Cr = s.M + (long long)i * NB * ld + (long long)k * NB;
+#pragma unroll
+        for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++)
+                cin[mb][nb] = *(const double2*)&Cr[(long long)FRAG_ROW(wm, mb, lane) * ld + FRAG_COL(wn, nb, lane)];
+    }
+    {
+        // rows of block i / cols of block k beyond the cell's size are padding; of the diagonal tile only
+        // the lower triangle is needed (the warp above the diagonal idles)
+        SubRange sr{0, hi_lt(wm, s.n16 - i * NB), 0, hi_lt(wn, s.n16 - k * NB)};
+        if (i == k && wm < wn) sr.mhi = 0;
+        gemm_nt_stream(acc, s.M + (long long)i * NB * ld, ld, s.M + (long long)k * NB * ld, ld, 0, k * NB, smem,
+                       [sr](int) { return sr; });
+    }
     double* Cg = s.M + (long long)i * NB * ld + (long long)k * NB;
     if (i != k) {
 #pragma unroll
         for (int mb = 0; mb < 4; mb++)
 #pragma unroll
             for (int nb = 0; nb < 4; nb++) {
-                double2* p = (double2*)&Cg[(long long)FRAG_ROW(wm, mb, lane) * ld + FRAG_COL(wn, nb, lane)];
-                double2 v = *p;
+                double2 v = cin[mb][nb];
                 v.x -= acc[mb][nb][0]; v.y -= acc[mb][nb][1];
-                *p = v;
+                *(double2*)&Cg[(long long)FRAG_ROW(wm, mb, lane) * ld + FRAG_COL(wn, nb, lane)] = v;
             }
         return;
     }
     // ---- diagonal tile: T = A_kk - acc, factor + invert in shared memory ----
-    double* T = smem;              // [64][TD]
-    double* Xi = smem + NB * TD;   // [64][TD]  X[r][c] = (L^-1)[r][c]
+    double* T = smem;                    // [64][TS]  A_kk -> L_kk (lower)
+    double* W = smem + NB * TS;          // [64][TS]  L_kk^-1 (lower, zeros above)
+    double* sc = smem + 2 * NB * TS + warp * 64;   // per-warp 8x8 scratch
+    __shared__ int s_bad;
 #pragma unroll
     for (int mb = 0; mb < 4; mb++)
 #pragma unroll
         for (int nb = 0; nb < 4; nb++) {
             int r = FRAG_ROW(wm, mb, lane), c = FRAG_COL(wn, nb, lane);
-            double2 v = *(const double2*)&Cg[(long long)r * ld + c];
-            T[r * TD + c] = v.x - acc[mb][nb][0];
-            T[r * TD + c + 1] = v.y - acc[mb][nb][1];
+            T[r * TS + c] = cin[mb][nb].x - acc[mb][nb][0];
+            T[r * TS + c + 1] = cin[mb][nb].y - acc[mb][nb][1];
         }
+    for (int idx = tid; idx < NB * TS; idx += GEMM_THREADS) W[idx] = 0.0;
+    if (tid == 0) s_bad = 0;
     __syncthreads();
-    bool bad = false;
-    for (int c = 0; c < NB; c++) {
-        double d = T[c * TD + c];
-        // OpenBLAS potf2: `if (ajj <= 0) return j+1` -> LinAlgError; a NaN pivot is NOT an error
-        // there, it propagates (SMLII then returns NaN, not inf), so mirror exactly that.
-        if (d <= 0.0) { bad = true; break; }       // uniform across the CTA
-        double sq = sqrt(d), inv = 1.0 / sq;
-        __syncthreads();
-        if (tid > c && tid < NB) T[tid * TD + c] *= inv;
-        if (tid == c) T[c * TD + c] = sq;
-        __syncthreads();
-        int r = tid & 63;
-        if (r > c) {
-            double lrc = T[r * TD + c];
-            for (int c2 = c + 1 + (tid >> 6); c2 <= r; c2 += 2) T[r * TD + c2] -= lrc * T[c2 * TD + c];
-        }
-        __syncthreads();
-    }
-    if (bad) {
+    diag_factor_invert(T, W, sc, &s_bad, tid);
+#ifndef OI_EXP_SAMEBLOCK
+    if (s_bad) {
         if (tid == 0) *s.fail = 1;
         return;
     }
-    // inverse of the lower-triangular factor, one column per thread
-    if (tid < NB) {
-        const int b = tid;
-        for (int r = 0; r < b; r++) Xi[r * TD + b] = 0.0;
-        Xi[b * TD + b] = 1.0 / T[b * TD + b];
-        for (int r = b + 1; r < NB; r++) {
-            double s0 = 0.0, s1 = 0.0;
-            int jj = b;
-            for (; jj + 1 < r; jj += 2) {
-                s0 += T[r * TD + jj] * Xi[jj * TD + b];
-                s1 += T[r * TD + jj + 1] * Xi[(jj + 1) * TD + b];
-            }
-            if (jj < r) s0 += T[r * TD + jj] * Xi[jj * TD + b];
-            Xi[r * TD + b] = -(s0 + s1) / T[r * TD + r];
-        }
-    } else if (tid < NB + 32) {
+#endif
+    if (warp == 0) {
         // log-determinant part: sum_i log L_ii of this block (GPR_CS2S3.py:128), fixed order
-        int l = tid - NB;
-        double v = log(T[l * TD + l]) + log(T[(l + 32) * TD + l + 32]);
+        double v = log(T[lane * TS + lane]) + log(T[(lane + 32) * TS + lane + 32]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (l == 0) s.part[k] = v;
+        if (lane == 0) s.part[k] = v;
     }
-    __syncthreads();
     double* Dk = s.Dinv + (long long)k * OI_TILE;
     for (int idx = tid; idx < OI_TILE; idx += GEMM_THREADS) {
         int r = idx >> 6, c = idx & 63;
-        Dk[idx] = Xi[r * TD + c];
-        Cg[(long long)r * ld + c] = (c >= r) ? Xi[c * TD + r] : 0.0;
+        Dk[idx] = W[r * TS + c];
+        Cg[(long long)r * ld + c] = (c >= r) ? W[c * TS + r] : 0.0;
     }
 }
 
@@ -343,13 +482,18 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_chol_panel(const OiSlot* __res
     const OiSlot s = slots[blockIdx.y];
     const int i = k + 1 + blockIdx.x;
     if (i >= s.N) return;
-    if (*(volatile int*)s.fail) return;
+    if (OI_FAILED(s)) return;
     const long long ld = s.npad;
     double acc[4][4][2];
     ACC_ZERO(acc);
     double* Cg = s.M + (long long)i * NB * ld + (long long)k * NB;
-    gemm_nt_stream(acc, Cg, ld, s.Dinv + (long long)k * OI_TILE, NB, 0, NB, smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 1, wn = warp & 1;
+    {
+        // Dinv[k][nn][kk] is lower triangular: output column nn only needs kk <= nn
+        const int mhi = hi_lt(wm, s.n16 - i * NB);
+        gemm_nt_stream(acc, Cg, ld, s.Dinv + (long long)k * OI_TILE, NB, 0, NB, smem,
+                       [mhi, wn](int kk) { return SubRange{0, mhi, lo_ge(wn, kk), 4}; });
+    }
 #pragma unroll
     for (int mb = 0; mb < 4; mb++)
 #pragma unroll
@@ -367,7 +511,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_chol_panel(const OiSlot* __res
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_fwd(const OiSlot* __restrict__ slots, OiCellArrays ca, OiPacked pk, double t_pred) {
     const OiSlot s = slots[blockIdx.x];
-    if (*(volatile int*)s.fail) return;
+    if (OI_FAILED(s)) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool pred = ca.phase[s.cell] == OI_PH_PREDICT;
     const int nrhs = pred ? 2 : 1;
@@ -419,19 +563,20 @@ __global__ void __launch_bounds__(256) k_fwd(const OiSlot* __restrict__ slots, O
         }
         if (lane == 0) {
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-                sb[0][warp * 8 + q] = tv[kc + warp * 8 + q] - a0[q];
-                sb[1][warp * 8 + q] = vv[kc + warp * 8 + q] - a1[q];
-            }
+            for (int q = 0; q < 8; q++) { sb[0][warp * 8 + q] = a0[q]; sb[1][warp * 8 + q] = a1[q]; }
         }
-        __syncthreads();
-        // x_k = Dinv[k] * s  (lower-triangular 64x64 mat-vec), thread (rhs, row)
+        // x_k = Dinv[k] * b_k - sum_{c<kc} Ls[kc+r][c] x[c]   (lower-triangular 64x64 mat-vec), thread (rhs, row)
+        double dsum = 0.0;
         if (tid < NB * nrhs) {
             int rh = tid / NB, r = tid % NB;
             const double* D = s.Dinv + (long long)k * OI_TILE + r * NB;
-            double acc = 0.0;
-            for (int c = 0; c <= r; c++) acc += D[c] * sb[rh][c];
-            (rh ? vv : tv)[kc + r] = acc;
+            const double* bsrc = (rh ? vv : tv) + kc;
+            for (int c = 0; c <= r; c++) dsum += D[c] * bsrc[c];
+        }
+        __syncthreads();
+        if (tid < NB * nrhs) {
+            int rh = tid / NB, r = tid % NB;
+            (rh ? vv : tv)[kc + r] = dsum - sb[rh][r];
         }
         __syncthreads();
     }
@@ -457,7 +602,65 @@ __global__ void __launch_bounds__(256) k_fwd(const OiSlot* __restrict__ slots, O
 }
 
 // ------------------------------------------------------------------------------------------
-// kernel (3d): U = L^-T by block distance d:  W_ik = -L_ii^-1 * sum_{j=k}^{i-1} L_ij W_jk, i = k+d,
+// kernel (3c'): row scaling  Ls_ij = L_ii^-1 * L_ij  (i > j), in place, one launch for all tiles.
+// With it the forward substitution and the inverse need no per-step triangular solve:
+//   t_i = L_ii^-1 r_i - sum_{j<i} Ls_ij t_j            W_ik = -sum_{j=k}^{i-1} Ls_ij W_jk
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS) k_scale_rows(const OiSlot* __restrict__ slots, int row) {
+    extern __shared__ __align__(16) double smem[];
+    const OiSlot s = slots[blockIdx.y];
+    int i, j;
+    if (row >= 0) { i = row; j = blockIdx.x; }
+    else { tile_ij(blockIdx.x, i, j); i += 1; }   // strictly lower tiles: (i, j), 1 <= i < N, j < i
+    if (i >= s.N) return;
+    if (OI_FAILED(s)) return;
+    const long long ld = s.npad;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 1, wn = warp & 1;
+    double* TA = smem;             // Dinv_i [m][kk]
+    double* TB = smem + NB * TS;   // L_ij   [kk][n]
+    const double* Di = s.Dinv + (long long)i * OI_TILE;
+    double* Lg = s.M + (long long)i * NB * ld + (long long)j * NB;
+    for (int idx = tid; idx < OI_TILE / 2; idx += GEMM_THREADS) {
+        int r = idx >> 5, c = (idx & 31) * 2;
+        cp_async16(&TA[r * TS + c], &Di[r * NB + c]);
+        cp_async16(&TB[r * TS + c], &Lg[(long long)r * ld + c]);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    double acc[4][4][2];
+    ACC_ZERO(acc);
+    const int vi = s.n16 - i * NB;              // valid rows of block i
+    const int fr = lane >> 2, fc = lane & 3;
+    // out[m][n] = sum_kk Dinv_i[m][kk] L_ij[kk][n], Dinv_i lower triangular: row m needs kk <= m
+    for (int c = 0; c < NB && c < vi; c += KT) {
+        const int mlo = lo_ge(wm, c), mhi = hi_lt(wm, vi);
+#pragma unroll
+        for (int ks = 0; ks < KT / 4; ks++) {
+            double a[4], b[4];
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++) a[mb] = TA[(wm * 32 + mb * 8 + fr) * TS + c + ks * 4 + fc];
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++) b[nb] = TB[(c + ks * 4 + fc) * TS + wn * 32 + nb * 8 + fr];
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++)
+                if (mb >= mlo && mb < mhi) {
+#pragma unroll
+                    for (int nb = 0; nb < 4; nb++) dmma(acc[mb][nb], a[mb], b[nb]);
+                }
+        }
+    }
+#pragma unroll
+    for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) {
+            double2 v; v.x = acc[mb][nb][0]; v.y = acc[mb][nb][1];
+            *(double2*)&Lg[(long long)FRAG_ROW(wm, mb, lane) * ld + FRAG_COL(wn, nb, lane)] = v;
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel (3d): U = L^-T by block distance d:  W_ik = -sum_{j=k}^{i-1} Ls_ij W_jk, i = k+d,
 // stored transposed (U[k-block][i-block] = W_ik^T) so every later contraction stays NT.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GEMM_THREADS) k_trtri(const OiSlot* __restrict__ slots, const int* __restrict__ phase, int d) {
@@ -466,39 +669,38 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_trtri(const OiSlot* __restrict
     const int kb = blockIdx.x, i = kb + d;
     if (i >= s.N) return;
     if (phase[s.cell] == OI_PH_PREDICT) return;
-    if (*(volatile int*)s.fail) return;
+    if (OI_FAILED(s)) return;
     const long long ld = s.npad;
     double acc[4][4][2];
     ACC_ZERO(acc);
-    gemm_nt_stream(acc, s.M + (long long)i * NB * ld, ld, s.M + (long long)kb * NB * ld, ld, kb * NB, i * NB, smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 1, wn = warp & 1;
-    double* TA = smem;             // [nn][m]  = acc[m][nn]
-    double* TB = smem + NB * TS;   // [m'][kk] = Dinv[i][m'][kk]
+    {
+        // first K block is U_kk (upper triangular): column nn of the output only needs kk' >= nn;
+        // rows of block i beyond the cell's size are padding
+        const int mhi = hi_lt(wm, s.n16 - i * NB);
+        const int kfirst = kb * NB;
+        gemm_nt_stream(acc, s.M + (long long)i * NB * ld, ld, s.M + (long long)kb * NB * ld, ld, kb * NB, i * NB, smem,
+                       [mhi, wn, kfirst](int kk) {
+                           int c = kk - kfirst;
+                           return SubRange{0, mhi, 0, c < NB ? hi_lt(wn, c + KT) : 4};
+                       });
+    }
+    // transpose through shared memory, then coalesced stores: U[kb*64+nn][i*64+m] = -acc[m][nn]
+    double* TA = smem;             // [nn][m]
 #pragma unroll
     for (int mb = 0; mb < 4; mb++)
 #pragma unroll
         for (int nb = 0; nb < 4; nb++) {
             int r = FRAG_ROW(wm, mb, lane), c = FRAG_COL(wn, nb, lane);
-            TA[c * TS + r] = acc[mb][nb][0];
-            TA[(c + 1) * TS + r] = acc[mb][nb][1];
+            TA[c * TS + r] = -acc[mb][nb][0];
+            TA[(c + 1) * TS + r] = -acc[mb][nb][1];
         }
-    const double* Di = s.Dinv + (long long)i * OI_TILE;
+    __syncthreads();
+    double* Ug = s.M + (long long)kb * NB * ld + (long long)i * NB;
     for (int idx = tid; idx < OI_TILE / 2; idx += GEMM_THREADS) {
         int r = idx >> 5, c = (idx & 31) * 2;
-        *(double2*)&TB[r * TS + c] = *(const double2*)&Di[r * NB + c];
+        *(double2*)&Ug[(long long)r * ld + c] = *(const double2*)&TA[r * TS + c];
     }
-    __syncthreads();
-    ACC_ZERO(acc);
-    mma_chunk(acc, TA, TB, TS, TS, wm, wn, lane, NB / 4);
-    // acc[nn][m'] = (Dinv_i * S)[m'][nn];  U[kb*64+nn][i*64+m'] = -that
-    double* Ug = s.M + (long long)kb * NB * ld + (long long)i * NB;
-#pragma unroll
-    for (int mb = 0; mb < 4; mb++)
-#pragma unroll
-        for (int nb = 0; nb < 4; nb++) {
-            double2 v; v.x = -acc[mb][nb][0]; v.y = -acc[mb][nb][1];
-            *(double2*)&Ug[(long long)FRAG_ROW(wm, mb, lane) * ld + FRAG_COL(wn, nb, lane)] = v;
-        }
 }
 
 // kernel (3e): alpha = K^-1 (y-m) = U t   (rows of U dotted with t), 64 rows per CTA
@@ -507,7 +709,7 @@ __global__ void __launch_bounds__(256) k_alpha(const OiSlot* __restrict__ slots,
     const int rb = blockIdx.x;
     if (rb >= s.N) return;
     if (phase[s.cell] == OI_PH_PREDICT) return;
-    if (*(volatile int*)s.fail) return;
+    if (OI_FAILED(s)) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ld = s.npad;
     const double* tv = s.vec;
@@ -538,27 +740,48 @@ __global__ void __launch_bounds__(256) k_alpha(const OiSlot* __restrict__ slots,
 // dK/dtheta is recomputed from the coordinates in registers; K^-1 is never stored.
 // Each tile writes five partial sums; off-diagonal tiles count twice (symmetry).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEMM_THREADS) k_lauum_trace(const OiSlot* __restrict__ slots, OiCellArrays ca, OiPacked pk) {
+__global__ void __launch_bounds__(GEMM_THREADS) k_lauum_trace(const OiSlot* __restrict__ slots, OiCellArrays ca, OiPacked pk, int row) {
     extern __shared__ __align__(16) double smem[];
     const OiSlot s = slots[blockIdx.y];
     int i, j;
-    tile_ij(blockIdx.x, i, j);
+    if (row >= 0) { i = row; j = blockIdx.x; }
+    else tile_ij(blockIdx.x, i, j);
     if (i >= s.N) return;
     if (ca.phase[s.cell] == OI_PH_PREDICT) return;
-    if (*(volatile int*)s.fail) return;
+    if (OI_FAILED(s)) return;
     const long long ld = s.npad;
     double acc[4][4][2];
     ACC_ZERO(acc);
-    gemm_nt_stream(acc, s.M + (long long)i * NB * ld, ld, s.M + (long long)j * NB * ld, ld, i * NB, s.npad, smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 1, wn = warp & 1;
-    // per-point data of the 64 rows and 64 cols: u (3), v (3), alpha
-    double(*P)[7][NB] = (double(*)[7][NB])smem;    // P[0]=rows, P[1]=cols
     const double* h = ca.hyp + 5 * (size_t)s.cell;
+    double praw[4] = {0, 0, 0, 0};              // this thread's point (row or col of the tile): x, y, t, alpha
+    {
+        int g = ((tid / NB) ? j : i) * NB + tid % NB;
+        if (g < s.n) {
+            praw[0] = pk.x[s.pt_off + g]; praw[1] = pk.y[s.pt_off + g]; praw[2] = pk.t[s.pt_off + g];
+            praw[3] = s.vec[2 * (long long)s.npad + g];
+        }
+    }
+    {
+        // K range ends at the cell's real size (rounded to 16); the first K block is U_ii (upper triangular):
+        // row m only needs kk' >= m (for the diagonal tile likewise column n, and the warp above the diagonal idles)
+        const int mhi0 = (i == j && wm < wn) ? 0 : hi_lt(wm, s.n16 - i * NB), nhi0 = hi_lt(wn, s.n16 - j * NB);
+        const int kfirst = i * NB;
+        const bool diag = (i == j);
+        gemm_nt_stream(acc, s.M + (long long)i * NB * ld, ld, s.M + (long long)j * NB * ld, ld, i * NB, s.n16, smem,
+                       [mhi0, nhi0, wm, wn, kfirst, diag](int kk) {
+                           int c = kk - kfirst;
+                           if (c >= NB) return SubRange{0, mhi0, 0, nhi0};
+                           int mh = min(mhi0, hi_lt(wm, c + KT));
+                           int nh = diag ? min(nhi0, hi_lt(wn, c + KT)) : nhi0;
+                           return SubRange{0, mh, 0, nh};
+                       });
+    }
+    // per-point data of the 64 rows and 64 cols: u (3), v (3), alpha (raw values were fetched before the K loop)
+    double(*P)[7][NB] = (double(*)[7][NB])smem;    // P[0]=rows, P[1]=cols
     {
         int which = tid / NB, q = tid % NB;        // 128 threads: rows then cols
-        int g = (which ? j : i) * NB + q;
-        double x = 0, y = 0, t = 0, a = 0;
-        if (g < s.n) { x = pk.x[s.pt_off + g]; y = pk.y[s.pt_off + g]; t = pk.t[s.pt_off + g]; a = s.vec[2 * (long long)s.npad + g]; }
+        double x = praw[0], y = praw[1], t = praw[2], a = praw[3];
         P[which][0][q] = (ROOT3 * x) / h[0]; P[which][1][q] = (ROOT3 * y) / h[1]; P[which][2][q] = (ROOT3 * t) / h[2];
         // np.sqrt(3.)*(x[:,theta]/ell[theta])  (GPR_CS2S3.py:97): divide, then multiply
         P[which][3][q] = ROOT3 * (x / h[0]); P[which][4][q] = ROOT3 * (y / h[1]); P[which][5][q] = ROOT3 * (t / h[2]);
@@ -574,12 +797,13 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_lauum_trace(const OiSlot* __re
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 const int c = FRAG_COL(wn, nb, lane) + e, gj = j * NB + c;
-                if (gi < s.n && gj < s.n) {
+                if (gi < s.n && gj < s.n && gj <= gi) {
                     double Qm = acc[mb][nb][e] - P[0][6][r] * P[1][6][c];
                     if (gi == gj) {
                         // Q = 0: dK_theta = 0, K = sf2
                         S[3] += Qm; S[4] += Qm;
                     } else {
+                        Qm *= 2.0;          // (gi, gj) and (gj, gi): K^-1, alpha alpha^T and dK are symmetric
                         double Q = pair_Q(P[0][0][r] - P[1][0][c], P[0][1][r] - P[1][1][c], P[0][2][r] - P[1][2][c]);
                         double E = exp(-Q);
                         double qx = P[0][3][r] - P[1][3][c], qy = P[0][4][r] - P[1][4][c], qt = P[0][5][r] - P[1][5][c];
@@ -602,8 +826,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_lauum_trace(const OiSlot* __re
     __syncthreads();
     if (tid < 5) {
         double v = ((red[tid][0] + red[tid][1]) + red[tid][2]) + red[tid][3];
-        if (tid < 4 && i != j) v *= 2.0;
-        s.part[s.N + 8 + 5 * (long long)blockIdx.x + tid] = v;
+        s.part[s.N + 8 + 5 * (long long)(i * (i + 1) / 2 + j) + tid] = v;
     }
 }
 
@@ -615,7 +838,8 @@ static void set_attrs() {
     if (g_attr_done) return;
     cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_CHOL);
     cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_BYTES);
-    cudaFuncSetAttribute(k_trtri, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_TRTRI);
+    cudaFuncSetAttribute(k_trtri, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_BYTES);
+    cudaFuncSetAttribute(k_scale_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_TRTRI);
     cudaFuncSetAttribute(k_lauum_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_BYTES);
     g_attr_done = true;
 }
@@ -636,30 +860,47 @@ void oi_launch_pack(const int* indices, long long total, const double* ox, const
     if (total <= 0) return;
     k_pack<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(indices, total, ox, oy, ot, oz, mean, px, py, pt, pr);
 }
-void oi_launch_build(const OiSlot* slots, int A, int Nmax, OiCellArrays ca, OiPacked pk, cudaStream_t st) {
-    k_build<<<dim3(Nmax * (Nmax + 1) / 2, A), 256, 0, st>>>(slots, ca, pk);
+// Slots are sorted by descending size, so the cells that own block row/column x are the prefix cnt_gt[x]
+// (number of slots with N > x): every grid below is exact in the slot dimension.  Big batches launch
+// the tile-parallel kernels one block row at a time (exact in both dimensions); small batches (the
+// optimiser's tail) use one 2-D launch to save launch latency.
+#define OI_ROWWISE_MIN_SLOTS 96
+void oi_launch_build(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, OiCellArrays ca, OiPacked pk, cudaStream_t st) {
+    if (A >= OI_ROWWISE_MIN_SLOTS) {
+        for (int i = 0; i < Nmax; i++) k_build<<<dim3(i + 1, cnt_gt[i]), 256, 0, st>>>(slots, ca, pk, i);
+    } else k_build<<<dim3(Nmax * (Nmax + 1) / 2, A), 256, 0, st>>>(slots, ca, pk, -1);
 }
-void oi_launch_chol_update(const OiSlot* slots, int A, int Nmax, int k, cudaStream_t st) {
+void oi_launch_chol_update(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int k, cudaStream_t st) {
     set_attrs();
-    k_chol_update<<<dim3(Nmax - k, A), GEMM_THREADS, OI_SMEM_CHOL, st>>>(slots, k);
+    k_chol_update<<<dim3(k == 0 ? 1 : Nmax - k, cnt_gt[k]), GEMM_THREADS, OI_SMEM_CHOL, st>>>(slots, k);
 }
-void oi_launch_chol_panel(const OiSlot* slots, int A, int Nmax, int k, cudaStream_t st) {
+void oi_launch_chol_panel(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int k, cudaStream_t st) {
     set_attrs();
-    if (Nmax - k - 1 <= 0) return;
-    k_chol_panel<<<dim3(Nmax - k - 1, A), GEMM_THREADS, PIPE_BYTES, st>>>(slots, k);
+    if (Nmax - k - 1 <= 0 || cnt_gt[k + 1] <= 0) return;
+    k_chol_panel<<<dim3(Nmax - k - 1, cnt_gt[k + 1]), GEMM_THREADS, PIPE_BYTES, st>>>(slots, k);
 }
 void oi_launch_fwd(const OiSlot* slots, int A, OiCellArrays ca, OiPacked pk, double t_pred, cudaStream_t st) {
     k_fwd<<<A, 256, 0, st>>>(slots, ca, pk, t_pred);
 }
-void oi_launch_trtri(const OiSlot* slots, int A, int Nmax, int d, const int* phase, cudaStream_t st) {
+void oi_launch_trtri(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int d, const int* phase, cudaStream_t st) {
     set_attrs();
-    if (Nmax - d <= 0) return;
-    k_trtri<<<dim3(Nmax - d, A), GEMM_THREADS, OI_SMEM_TRTRI, st>>>(slots, phase, d);
+    if (Nmax - d <= 0 || cnt_gt[d] <= 0) return;
+    k_trtri<<<dim3(Nmax - d, cnt_gt[d]), GEMM_THREADS, PIPE_BYTES, st>>>(slots, phase, d);
+}
+void oi_launch_scale_rows(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, cudaStream_t st) {
+    set_attrs();
+    if (Nmax < 2) return;
+    if (A >= OI_ROWWISE_MIN_SLOTS) {
+        for (int i = 1; i < Nmax; i++) k_scale_rows<<<dim3(i, cnt_gt[i]), GEMM_THREADS, OI_SMEM_TRTRI, st>>>(slots, i);
+    } else k_scale_rows<<<dim3(Nmax * (Nmax - 1) / 2, A), GEMM_THREADS, OI_SMEM_TRTRI, st>>>(slots, -1);
 }
 void oi_launch_alpha(const OiSlot* slots, int A, int Nmax, const int* phase, cudaStream_t st) {
     k_alpha<<<dim3(Nmax, A), 256, 0, st>>>(slots, phase);
 }
-void oi_launch_lauum_trace(const OiSlot* slots, int A, int Nmax, OiCellArrays ca, OiPacked pk, cudaStream_t st) {
+void oi_launch_lauum_trace(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, OiCellArrays ca, OiPacked pk, cudaStream_t st) {
     set_attrs();
-    k_lauum_trace<<<dim3(Nmax * (Nmax + 1) / 2, A), GEMM_THREADS, PIPE_BYTES, st>>>(slots, ca, pk);
+    if (A >= OI_ROWWISE_MIN_SLOTS) {
+        for (int i = 0; i < Nmax; i++)
+            k_lauum_trace<<<dim3(i + 1, cnt_gt[i]), GEMM_THREADS, PIPE_BYTES, st>>>(slots, ca, pk, i);
+    } else k_lauum_trace<<<dim3(Nmax * (Nmax + 1) / 2, A), GEMM_THREADS, PIPE_BYTES, st>>>(slots, ca, pk, -1);
 }

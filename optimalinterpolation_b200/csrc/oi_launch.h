@@ -4,7 +4,7 @@
 #include "oi_types.h"
 
 #define TILE_PER_THREAD_256 (OI_TILE / 256)
-#define OI_SMEM_CHOL (2 * OI_NB * 65 * 8)     // T + X of the diagonal factor (>= the cp.async pipeline)
+#define OI_SMEM_CHOL (2 * OI_NB * 68 * 8 + 4 * 64 * 8)   // T + W of the diagonal factor + per-warp scratch (>= the cp.async pipeline)
 #define OI_SMEM_TRTRI (2 * OI_NB * 68 * 8)    // two resident 64x64 tiles (>= the cp.async pipeline)
 
 void oi_launch_count(const double* ox, const double* oy, int n_obs, const double* X, int n_cells, double r2, int* counts,
@@ -14,13 +14,14 @@ void oi_launch_fill(const double* ox, const double* oy, int n_obs, const double*
                     const long long* offsets, int* indices, cudaStream_t st);
 void oi_launch_pack(const int* indices, long long total, const double* ox, const double* oy, const double* ot,
                     const double* oz, double mean, double* px, double* py, double* pt, double* pr, cudaStream_t st);
-void oi_launch_build(const OiSlot* slots, int A, int Nmax, OiCellArrays ca, OiPacked pk, cudaStream_t st);
-void oi_launch_chol_update(const OiSlot* slots, int A, int Nmax, int k, cudaStream_t st);
-void oi_launch_chol_panel(const OiSlot* slots, int A, int Nmax, int k, cudaStream_t st);
+void oi_launch_build(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, OiCellArrays ca, OiPacked pk, cudaStream_t st);
+void oi_launch_chol_update(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int k, cudaStream_t st);
+void oi_launch_chol_panel(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int k, cudaStream_t st);
+void oi_launch_scale_rows(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, cudaStream_t st);
 void oi_launch_fwd(const OiSlot* slots, int A, OiCellArrays ca, OiPacked pk, double t_pred, cudaStream_t st);
-void oi_launch_trtri(const OiSlot* slots, int A, int Nmax, int d, const int* phase, cudaStream_t st);
+void oi_launch_trtri(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int d, const int* phase, cudaStream_t st);
 void oi_launch_alpha(const OiSlot* slots, int A, int Nmax, const int* phase, cudaStream_t st);
-void oi_launch_lauum_trace(const OiSlot* slots, int A, int Nmax, OiCellArrays ca, OiPacked pk, cudaStream_t st);
+void oi_launch_lauum_trace(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, OiCellArrays ca, OiPacked pk, cudaStream_t st);
 
 // oi_optim.cu
 struct OiRunConst {

@@ -18,6 +18,7 @@ struct OiSlot {
     int* fail;        // set when a Cholesky pivot is <= 0 or NaN (np.linalg.LinAlgError in the reference)
     long long pt_off; // offset of this cell's points in the packed (CSR-ordered) coordinate arrays
     int cell, n, npad, N;
+    int n16, pad_;    // n rounded up to the DMMA K chunk (16): K loops and edge sub-tiles stop here
 };
 
 struct OiCellArrays {
