@@ -2,9 +2,9 @@
 """bench.py -- GP cells/sec (fit + predict) on the synthetic 25 km pan-Arctic day (BASELINE.json).
 
 A step = one pass of the hot path (neighbour gather -> lockstep CG fit -> posterior) over one batch
-of cells: ``--gpus N`` stripes of the day (stripe s = every 16th ice cell starting at s, so each
-stripe has the day's n-histogram; ~1195 cells per stripe, per-GPU work fixed => weak scaling;
-at N=8 one step is half the day).  Cells of a step are sharded over ranks by LPT on n^3
+of cells: ``2 x --gpus N`` stripes of the day (stripe s = every 16th ice cell starting at s, so each
+stripe has the day's n-histogram; ~1195 cells per stripe, 2 stripes = 1/8 day per GPU and step,
+per-GPU work fixed => weak scaling; at N=8 one step is the whole day).  Cells of a step are sharded over ranks by LPT on n^3
 (optimalinterpolation_b200/shard.py); the only collective is the final gather of the result rows.
 
   value : cells/s with observations + cell coordinates already resident in HBM (timed: gather +
@@ -33,10 +33,10 @@ N_STRIPES = 16
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--stripes-per-gpu", type=int, default=1)
+    ap.add_argument("--stripes-per-gpu", type=int, default=2)
     ap.add_argument("--max-active", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frac", type=float, default=0.2, help="cheapest fraction of cells the CPU sample is drawn from")
