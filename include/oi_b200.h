@@ -58,7 +58,7 @@ typedef struct oi_params {
     double gtol;            /* 0 => 1e-5 (scipy default)                                                */
     double scratch_gib;     /* device scratch budget for the lockstep batch, 0 => automatic             */
     int32_t max_active;     /* maximum cells evaluated per lockstep iteration, 0 => automatic           */
-    int32_t reserved;
+    int32_t n_groups;       /* independent lockstep groups (one CUDA stream each) whose kernels overlap, 0 => automatic */
 } oi_params;
 
 typedef struct oi_stats {
@@ -74,6 +74,7 @@ typedef struct oi_stats {
     double ms_build, ms_chol, ms_fwd, ms_trtri, ms_alpha, ms_lauum, ms_finalize;  /* per kernel family   */
     double flops_chol, flops_trtri, flops_lauum;   /* n^3/3 each per evaluation            */
     int64_t launches_chol, launches_trtri, launches_lauum;
+    int64_t n_groups;       /* lockstep groups used; with > 1 the per-family ms_* are per-stream times that overlap */
 } oi_stats;
 
 int  oi_version(void);

@@ -18,7 +18,7 @@ class OiParams(C.Structure):
     _fields_ = [("radius_m", C.c_double), ("t_pred", C.c_double), ("prior_mean", C.c_double),
                 ("n_hyp", C.c_int32), ("mode", C.c_int32), ("grad_convention", C.c_int32), ("maxiter", C.c_int32),
                 ("x0", C.c_double * 6), ("gtol", C.c_double), ("scratch_gib", C.c_double),
-                ("max_active", C.c_int32), ("reserved", C.c_int32)]
+                ("max_active", C.c_int32), ("n_groups", C.c_int32)]
 
 
 class OiStats(C.Structure):
@@ -28,7 +28,8 @@ class OiStats(C.Structure):
                 ("ms_build", C.c_double), ("ms_chol", C.c_double), ("ms_fwd", C.c_double), ("ms_trtri", C.c_double),
                 ("ms_alpha", C.c_double), ("ms_lauum", C.c_double), ("ms_finalize", C.c_double),
                 ("flops_chol", C.c_double), ("flops_trtri", C.c_double), ("flops_lauum", C.c_double),
-                ("launches_chol", C.c_int64), ("launches_trtri", C.c_int64), ("launches_lauum", C.c_int64)]
+                ("launches_chol", C.c_int64), ("launches_trtri", C.c_int64), ("launches_lauum", C.c_int64),
+                ("n_groups", C.c_int64)]
 
 
 _lib = None

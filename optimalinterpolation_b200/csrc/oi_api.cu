@@ -50,10 +50,13 @@ struct oi_handle {
     int *d_slot_phase = nullptr, *h_slot_phase = nullptr, *d_fail = nullptr;
     int slot_cap = 0;
     cudaEvent_t ev[10]{};
+    std::vector<struct OiGroup*> groups;
     oi_stats stats{};
     bool have_results = false;
 };
 
+struct OiGroup;
+static void free_groups(oi_handle* h);
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static size_t slot_bytes(int n) {
@@ -114,6 +117,7 @@ extern "C" void oi_destroy(oi_handle* h) {
     cudaFree(h->indices); cudaFree(h->px); cudaFree(h->py); cudaFree(h->pt); cudaFree(h->pr);
     cudaFree(h->arena); cudaFree(h->d_slots); cudaFree(h->d_slot_phase); cudaFree(h->d_fail);
     cudaFreeHost(h->h_slots); cudaFreeHost(h->h_slot_phase);
+    free_groups(h);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->own_st) cudaStreamDestroy(h->own_st);
     delete h;
@@ -207,8 +211,31 @@ extern "C" int oi_get_neighbours(oi_handle* h, int64_t* offsets, int32_t* indice
 
 // ------------------------------------------------------------------------------------------
 // the lockstep batch scheduler
+//
+// The active cells are split into G independent GROUPS, each with its own CUDA stream, slot table and
+// share of the scratch arena.  A group runs lockstep iterations (build -> Cholesky -> ... -> finalize ->
+// D2H of the new phases) on its stream; the host services the groups round-robin, so while it retires
+// and refills group g the other G-1 groups' kernel chains are already queued.  Kernels of different
+// groups overlap on the device: the low-parallelism launches of one group (last block columns of the
+// factorisation, large block distances of the inverse, the optimiser's tail with a handful of cells)
+// fill with tiles of the others.  A cell's numbers do not depend on its group or its batch
+// (fixed-order reductions), so results are bit-identical for every G.
 // ------------------------------------------------------------------------------------------
-static int ensure_batch_buffers(oi_handle* h, size_t want_arena, int want_slots) {
+struct OiGroup {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[8]{};            // family boundaries of the iteration in flight
+    cudaEvent_t done = nullptr;
+    OiSlot *d_slots = nullptr, *h_slots = nullptr;
+    int *d_slot_phase = nullptr, *h_slot_phase = nullptr, *d_fail = nullptr;
+    char* arena = nullptr; size_t arena_bytes = 0, used = 0;
+    int slot_cap = 0;
+    std::vector<int> active, cnt_gt;
+    bool in_flight = false;
+    int A = 0, Nmax = 0;
+    double fl = 0, flf = 0, flf_chol = 0, flf_fit = 0; int64_t nev = 0;
+};
+
+static int ensure_batch_buffers(oi_handle* h, size_t want_arena, int want_slots, int G) {
     if (want_arena > h->arena_bytes) {
         cudaFree(h->arena); h->arena = nullptr; h->arena_bytes = 0;
         CK(cudaMalloc(&h->arena, want_arena));
@@ -224,15 +251,139 @@ static int ensure_batch_buffers(oi_handle* h, size_t want_arena, int want_slots)
         CK(cudaMallocHost(&h->h_slot_phase, (size_t)want_slots * 4));
         h->slot_cap = want_slots;
     }
+    while ((int)h->groups.size() < G) {
+        OiGroup* g = new OiGroup();
+        CK(cudaStreamCreateWithFlags(&g->st, cudaStreamNonBlocking));
+        for (auto& e : g->ev) CK(cudaEventCreate(&e));
+        CK(cudaEventCreateWithFlags(&g->done, cudaEventDisableTiming));
+        h->groups.push_back(g);
+    }
     return OI_OK;
 }
+
+static void free_groups(oi_handle* h) {
+    for (OiGroup* g : h->groups) {
+        for (auto& e : g->ev) if (e) cudaEventDestroy(e);
+        if (g->done) cudaEventDestroy(g->done);
+        if (g->st) cudaStreamDestroy(g->st);
+        delete g;
+    }
+    h->groups.clear();
+}
+
+struct LockstepRun {
+    oi_handle* h; std::vector<int>& h_phase; const OiRunConst& rc; double t_pred;
+    std::vector<int> pending; size_t next = 0;
+    OiPacked pk; FILE* trace = nullptr;
+    double ms_factor = 0;
+
+    // admit pending cells (largest first) into group g, pack its slot table and queue one iteration
+    int issue(OiGroup& g, int gi) {
+        while (next < pending.size() && (int)g.active.size() < g.slot_cap) {
+            size_t need = slot_bytes(h->h_counts[pending[next]]);
+            if (g.used + need > g.arena_bytes) break;
+            g.used += need; g.active.push_back(pending[next++]);
+        }
+        g.in_flight = false;
+        if (g.active.empty()) return OI_OK;
+        const int A = (int)g.active.size();
+        size_t off = 0;
+        int Nmax = 0;
+        g.fl = g.flf = g.flf_chol = g.flf_fit = 0; g.nev = 0;
+        // slots are kept in descending size so that the cells owning block row x are a prefix
+        std::stable_sort(g.active.begin(), g.active.end(), [&](int a, int b) { return h->h_counts[a] > h->h_counts[b]; });
+        for (int a = 0; a < A; a++) {
+            int c = g.active[a], n = h->h_counts[c];
+            int N = (n + OI_NB - 1) / OI_NB, npad = N * OI_NB;
+            OiSlot& s = g.h_slots[a];
+            s.M = (double*)(g.arena + off); off += align_up((size_t)npad * npad * 8, 256);
+            s.Dinv = (double*)(g.arena + off); off += align_up((size_t)N * OI_TILE * 8, 256);
+            s.vec = (double*)(g.arena + off); off += align_up((size_t)3 * npad * 8, 256);
+            s.part = (double*)(g.arena + off); off += align_up((size_t)(N + 8 + 5 * N * (N + 1) / 2) * 8, 256);
+            s.fail = g.d_fail + a;
+            s.pt_off = h->h_offsets[c];
+            s.cell = c; s.n = n; s.npad = npad; s.N = N; s.n16 = (n + 15) / 16 * 16; s.pad_ = 0;
+            Nmax = std::max(Nmax, N);
+            double dn = n;
+            g.flf_chol += dn * dn * dn / 3;
+            if (h_phase[c] == OI_PH_PREDICT) { g.fl += dn * dn * dn / 3 + 19 * dn * dn; g.flf += dn * dn * dn / 3; }
+            else { g.fl += dn * dn * dn + 22 * dn * dn; g.flf += dn * dn * dn; g.flf_fit += dn * dn * dn; g.nev++; }
+        }
+        // cnt_gt[x] = number of (size-sorted) slots with more than x blocks
+        g.cnt_gt.assign((size_t)Nmax + 2, 0);
+        for (int a = 0; a < A; a++) g.cnt_gt[g.h_slots[a].N]++;                      // histogram of N
+        for (int x = Nmax; x >= 0; x--) g.cnt_gt[x] = g.cnt_gt[x + 1] + g.cnt_gt[x];  // -> #slots with N >= x
+        for (int x = 0; x <= Nmax; x++) g.cnt_gt[x] = g.cnt_gt[x + 1];                // -> #slots with N > x
+        const int* cg = g.cnt_gt.data();
+        cudaStream_t st = g.st;
+        CK(cudaMemcpyAsync(g.d_slots, g.h_slots, (size_t)A * sizeof(OiSlot), cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(g.ev[0], st));
+        oi_launch_build(g.d_slots, A, Nmax, cg, h->ca, pk, st);
+        CK(cudaEventRecord(g.ev[1], st));
+        for (int k = 0; k < Nmax; k++) {
+            oi_launch_chol_update(g.d_slots, A, Nmax, cg, k, st);
+            oi_launch_chol_panel(g.d_slots, A, Nmax, cg, k, st);
+        }
+        oi_launch_scale_rows(g.d_slots, A, Nmax, cg, st);
+        CK(cudaEventRecord(g.ev[2], st));
+        oi_launch_fwd(g.d_slots, A, h->ca, pk, t_pred, st);
+        CK(cudaEventRecord(g.ev[3], st));
+        for (int d = 1; d < Nmax; d++) oi_launch_trtri(g.d_slots, A, Nmax, cg, d, h->ca.phase, st);
+        CK(cudaEventRecord(g.ev[4], st));
+        oi_launch_alpha(g.d_slots, A, Nmax, h->ca.phase, st);
+        CK(cudaEventRecord(g.ev[5], st));
+        oi_launch_lauum_trace(g.d_slots, A, Nmax, cg, h->ca, pk, st);
+        CK(cudaEventRecord(g.ev[6], st));
+        oi_launch_finalize(g.d_slots, A, h->ca, rc, g.d_slot_phase, st);
+        CK(cudaEventRecord(g.ev[7], st));
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(g.h_slot_phase, g.d_slot_phase, (size_t)A * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(g.done, st));
+        g.A = A; g.Nmax = Nmax; g.in_flight = true;
+        (void)gi;
+        return OI_OK;
+    }
+
+    // wait for group g's iteration, account for it, retire the finished cells
+    int retire(OiGroup& g, int gi) {
+        CK(cudaEventSynchronize(g.done));
+        float m[7];
+        for (int q = 0; q < 7; q++) cudaEventElapsedTime(&m[q], g.ev[q], g.ev[q + 1]);
+        oi_stats& S = h->stats;
+        S.ms_build += m[0]; S.ms_chol += m[1]; S.ms_fwd += m[2]; S.ms_trtri += m[3];
+        S.ms_alpha += m[4]; S.ms_lauum += m[5]; S.ms_finalize += m[6];
+        ms_factor += m[1] + m[3] + m[5];
+        const int A = g.A, Nmax = g.Nmax;
+        if (trace) std::fprintf(trace, "%lld,%d,%d,%d,%.4f,%.4f,%.4f,%.4f,%.4f,%.4f,%.4f,%.6g\n", (long long)S.n_iterations, gi, A, Nmax,
+                                m[0], m[1], m[2], m[3], m[4], m[5], m[6], g.flf);
+        S.flops += g.fl; S.flops_factor += g.flf; S.n_evals += g.nev;
+        S.flops_chol += g.flf_chol; S.flops_trtri += g.flf_fit / 3; S.flops_lauum += g.flf_fit / 3;
+        const bool roww = A >= OI_ROWWISE_MIN_SLOTS_HOST;
+        S.launches_chol += 2 * Nmax - 1 + (Nmax > 1 ? (roww ? Nmax - 1 : 1) : 0);
+        S.launches_trtri += std::max(0, Nmax - 1); S.launches_lauum += roww ? Nmax : 1;
+        S.n_iterations++;
+        S.n_launches += (roww ? Nmax : 1) + (2 * Nmax - 1) + (Nmax > 1 ? (roww ? Nmax - 1 : 1) : 0) + 1 + std::max(0, Nmax - 1) + 1 +
+                        (roww ? Nmax : 1) + 1;
+        size_t w = 0;
+        for (int a = 0; a < A; a++) {
+            int c = g.active[a];
+            h_phase[c] = g.h_slot_phase[a];
+            if (h_phase[c] == OI_PH_DONE) g.used -= slot_bytes(h->h_counts[c]);
+            else g.active[w++] = c;
+        }
+        g.active.resize(w);
+        g.in_flight = false;
+        return OI_OK;
+    }
+};
 
 // Runs lockstep iterations until every cell with observations reaches OI_PH_DONE.
 // h_phase: host copy of the initial per-cell phase (already uploaded to ca.phase).
 static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunConst& rc, double t_pred,
-                        double scratch_gib, int max_active) {
+                        double scratch_gib, int max_active, int n_groups) {
     const int nc = (int)h->n_cells;
-    std::vector<int> pending;
+    LockstepRun R{h, h_phase, rc, t_pred};
+    std::vector<int>& pending = R.pending;
     pending.reserve(nc);
     size_t biggest = 0;
     for (int c = 0; c < nc; c++)
@@ -242,6 +393,9 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
     if (pending.empty()) return OI_OK;
     if (max_active <= 0) max_active = 2048;
     max_active = std::min<int>(max_active, 65535);
+    if (const char* e = std::getenv("OI_GROUPS")) n_groups = std::atoi(e);
+    if (n_groups <= 0) n_groups = OI_DEFAULT_GROUPS;
+    int G = std::max(1, std::min(n_groups, 16));
     size_t want;
     if (scratch_gib > 0) want = (size_t)(scratch_gib * 1073741824.0);
     else {
@@ -252,108 +406,55 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
     }
     size_t all = 0;
     for (int c : pending) all += slot_bytes(h->h_counts[c]);
-    want = std::min(want, all);          // never more than everything resident
-    want = std::max(want, biggest);
-    int rcode = ensure_batch_buffers(h, want, std::min<int>(max_active, (int)pending.size()));
+    want = std::min(want, all + (size_t)G * 256);      // never more than everything resident
+    while (G > 1 && want / G < biggest) G--;            // every group must be able to hold the largest cell
+    want = std::max(want, biggest * G);
+    const int total_slots = std::min<int>(max_active, (int)pending.size());
+    const int per = (total_slots + G - 1) / G;
+    int rcode = ensure_batch_buffers(h, want, per * G, G);
     if (rcode) return rcode;
-
-    OiPacked pk{h->px, h->py, h->pt, h->pr};
-    // OI_TRACE=<file>: one CSV line per lockstep iteration (active cells, Nmax, ms per kernel family)
-    FILE* trace = nullptr;
+    const size_t share = (h->arena_bytes / G) & ~(size_t)255;
+    for (int gi = 0; gi < G; gi++) {
+        OiGroup& g = *h->groups[gi];
+        g.arena = h->arena + (size_t)gi * share; g.arena_bytes = share; g.used = 0;
+        g.d_slots = h->d_slots + (size_t)gi * per; g.h_slots = h->h_slots + (size_t)gi * per;
+        g.d_slot_phase = h->d_slot_phase + (size_t)gi * per; g.h_slot_phase = h->h_slot_phase + (size_t)gi * per;
+        g.d_fail = h->d_fail + (size_t)gi * per;
+        g.slot_cap = per; g.active.clear(); g.in_flight = false;
+    }
+    R.pk = OiPacked{h->px, h->py, h->pt, h->pr};
+    // OI_TRACE=<file>: one CSV line per group iteration (active cells, Nmax, stream-ms per kernel family)
     if (const char* tp = std::getenv("OI_TRACE")) {
-        trace = std::fopen(tp, "a");
-        if (trace) std::fprintf(trace, "iter,active,Nmax,ms_build,ms_chol,ms_fwd,ms_trtri,ms_alpha,ms_lauum,ms_finalize,flops_factor\n");
+        R.trace = std::fopen(tp, "a");
+        if (R.trace) std::fprintf(R.trace, "iter,group,active,Nmax,ms_build,ms_chol,ms_fwd,ms_trtri,ms_alpha,ms_lauum,ms_finalize,flops_factor\n");
     }
-    std::vector<int> active, cnt_gt;
-    size_t used = 0, next = 0;
-    double ms_factor = 0;
-    while (true) {
-        while (next < pending.size() && (int)active.size() < max_active) {
-            size_t need = slot_bytes(h->h_counts[pending[next]]);
-            if (used + need > h->arena_bytes) break;
-            used += need; active.push_back(pending[next++]);
+    // fork: the group streams start after everything queued on the handle's stream
+    CK(cudaEventRecord(h->ev[0], h->st));
+    for (int gi = 0; gi < G; gi++) CK(cudaStreamWaitEvent(h->groups[gi]->st, h->ev[0], 0));
+    int rc2 = OI_OK;
+    for (int gi = 0; gi < G && !rc2; gi++) rc2 = R.issue(*h->groups[gi], gi);
+    bool any = true;
+    while (!rc2 && any) {
+        any = false;
+        for (int gi = 0; gi < G && !rc2; gi++) {
+            OiGroup& g = *h->groups[gi];
+            if (!g.in_flight) continue;
+            any = true;
+            if ((rc2 = R.retire(g, gi))) break;
+            rc2 = R.issue(g, gi);
         }
-        if (active.empty()) {
-            if (next < pending.size()) return fail(OI_ERR_NOMEM, "run_lockstep: scratch arena too small for one cell");
-            break;
-        }
-        const int A = (int)active.size();
-        size_t off = 0;
-        int Nmax = 0;
-        double fl = 0, flf = 0, flf_chol = 0, flf_fit = 0;
-        int64_t nev = 0;
-        for (int a = 0; a < A; a++) {
-            int c = active[a], n = h->h_counts[c];
-            int N = (n + OI_NB - 1) / OI_NB, npad = N * OI_NB;
-            OiSlot& s = h->h_slots[a];
-            s.M = (double*)(h->arena + off); off += align_up((size_t)npad * npad * 8, 256);
-            s.Dinv = (double*)(h->arena + off); off += align_up((size_t)N * OI_TILE * 8, 256);
-            s.vec = (double*)(h->arena + off); off += align_up((size_t)3 * npad * 8, 256);
-            s.part = (double*)(h->arena + off); off += align_up((size_t)(N + 8 + 5 * N * (N + 1) / 2) * 8, 256);
-            s.fail = h->d_fail + a;
-            s.pt_off = 0;   // filled below from the CSR offsets
-            s.cell = c; s.n = n; s.npad = npad; s.N = N; s.n16 = (n + 15) / 16 * 16; s.pad_ = 0;
-            Nmax = std::max(Nmax, N);
-            double dn = n;
-            flf_chol += dn * dn * dn / 3;
-            if (h_phase[c] == OI_PH_PREDICT) { fl += dn * dn * dn / 3 + 19 * dn * dn; flf += dn * dn * dn / 3; }
-            else { fl += dn * dn * dn + 22 * dn * dn; flf += dn * dn * dn; flf_fit += dn * dn * dn; nev++; }
-        }
-        for (int a = 0; a < A; a++) h->h_slots[a].pt_off = h->h_offsets[active[a]];
-        // cnt_gt[x] = number of (size-sorted) slots with more than x blocks
-        cnt_gt.assign((size_t)Nmax + 2, 0);
-        for (int a = 0; a < A; a++) cnt_gt[h->h_slots[a].N]++;              // histogram of N
-        for (int x = Nmax; x >= 0; x--) cnt_gt[x] = cnt_gt[x + 1] + cnt_gt[x];  // -> #slots with N >= x
-        for (int x = 0; x <= Nmax; x++) cnt_gt[x] = cnt_gt[x + 1];             // -> #slots with N > x
-        const int* cg = cnt_gt.data();
-        CK(cudaMemcpyAsync(h->d_slots, h->h_slots, (size_t)A * sizeof(OiSlot), cudaMemcpyHostToDevice, h->st));
-        CK(cudaEventRecord(h->ev[0], h->st));
-        oi_launch_build(h->d_slots, A, Nmax, cg, h->ca, pk, h->st);
-        CK(cudaEventRecord(h->ev[1], h->st));
-        for (int k = 0; k < Nmax; k++) {
-            oi_launch_chol_update(h->d_slots, A, Nmax, cg, k, h->st);
-            oi_launch_chol_panel(h->d_slots, A, Nmax, cg, k, h->st);
-        }
-        oi_launch_scale_rows(h->d_slots, A, Nmax, cg, h->st);
-        CK(cudaEventRecord(h->ev[2], h->st));
-        oi_launch_fwd(h->d_slots, A, h->ca, pk, t_pred, h->st);
-        CK(cudaEventRecord(h->ev[3], h->st));
-        for (int d = 1; d < Nmax; d++) oi_launch_trtri(h->d_slots, A, Nmax, cg, d, h->ca.phase, h->st);
-        CK(cudaEventRecord(h->ev[4], h->st));
-        oi_launch_alpha(h->d_slots, A, Nmax, h->ca.phase, h->st);
-        CK(cudaEventRecord(h->ev[5], h->st));
-        oi_launch_lauum_trace(h->d_slots, A, Nmax, cg, h->ca, pk, h->st);
-        CK(cudaEventRecord(h->ev[6], h->st));
-        oi_launch_finalize(h->d_slots, A, h->ca, rc, h->d_slot_phase, h->st);
-        CK(cudaEventRecord(h->ev[7], h->st));
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(h->h_slot_phase, h->d_slot_phase, (size_t)A * 4, cudaMemcpyDeviceToHost, h->st));
-        CK(cudaStreamSynchronize(h->st));
-        float m[7];
-        for (int q = 0; q < 7; q++) cudaEventElapsedTime(&m[q], h->ev[q], h->ev[q + 1]);
-        h->stats.ms_build += m[0]; h->stats.ms_chol += m[1]; h->stats.ms_fwd += m[2]; h->stats.ms_trtri += m[3];
-        h->stats.ms_alpha += m[4]; h->stats.ms_lauum += m[5]; h->stats.ms_finalize += m[6];
-        ms_factor += m[1] + m[3] + m[5];
-        if (trace) std::fprintf(trace, "%lld,%d,%d,%.4f,%.4f,%.4f,%.4f,%.4f,%.4f,%.4f,%.6g\n", (long long)h->stats.n_iterations, A, Nmax,
-                                m[0], m[1], m[2], m[3], m[4], m[5], m[6], flf);
-        h->stats.flops += fl; h->stats.flops_factor += flf; h->stats.n_evals += nev;
-        h->stats.flops_chol += flf_chol; h->stats.flops_trtri += flf_fit / 3; h->stats.flops_lauum += flf_fit / 3;
-        h->stats.launches_chol += 2 * Nmax; h->stats.launches_trtri += std::max(0, Nmax - 1); h->stats.launches_lauum += 1;
-        h->stats.n_iterations++;
-        h->stats.n_launches += 1 + Nmax + std::max(0, Nmax - 1) + (Nmax > 1) + 1 + std::max(0, Nmax - 1) + 2 + 1;
-        // retire finished cells, keep the rest in (descending n) order
-        size_t w = 0;
-        for (int a = 0; a < A; a++) {
-            int c = active[a];
-            h_phase[c] = h->h_slot_phase[a];
-            if (h_phase[c] == OI_PH_DONE) used -= slot_bytes(h->h_counts[c]);
-            else active[w++] = c;
-        }
-        active.resize(w);
     }
-    h->stats.ms_factor += ms_factor;
-    if (trace) std::fclose(trace);
-    return OI_OK;
+    if (!rc2 && R.next < pending.size()) rc2 = fail(OI_ERR_NOMEM, "run_lockstep: scratch arena too small for one cell");
+    // join: the handle's stream continues after every group
+    for (int gi = 0; gi < G; gi++) {
+        cudaEventRecord(h->groups[gi]->done, h->groups[gi]->st);
+        cudaStreamWaitEvent(h->st, h->groups[gi]->done, 0);
+    }
+    if (rc2) cudaDeviceSynchronize();
+    h->stats.ms_factor += R.ms_factor;
+    h->stats.n_groups = G;
+    if (R.trace) std::fclose(R.trace);
+    return rc2;
 }
 
 static int pack_points(oi_handle* h, double mean) {
@@ -388,7 +489,7 @@ extern "C" int oi_nlml_grad(oi_handle* h, const double* hypers, int32_t n_hyp, d
     OiRunConst rc{};
     rc.mean = prior_mean; rc.gtol = 1e-5; rc.n_hyp = n_hyp; rc.grad_convention = grad_convention; rc.maxiter = 0;
     reset_stats(h);
-    r = run_lockstep(h, phase, rc, 0.0, 0.0, 0);
+    r = run_lockstep(h, phase, rc, 0.0, 0.0, 0, 0);
     if (r) return r;
     std::vector<double> f(nc), g((size_t)nc * OI_MAXH);
     CK(cudaMemcpy(f.data(), h->ca.evf, (size_t)nc * 8, cudaMemcpyDeviceToHost));
@@ -437,7 +538,7 @@ extern "C" int oi_run(oi_handle* h, const oi_params* p, const double* hypers_in)
         CK(cudaMemcpyAsync(h->ca.hyp, hypers_in, (size_t)nc * 40, cudaMemcpyHostToDevice, h->st));
     }
     CK(cudaStreamSynchronize(h->st));   // staging vectors go out of scope below
-    r = run_lockstep(h, phase, rc, p->t_pred, p->scratch_gib, p->max_active);
+    r = run_lockstep(h, phase, rc, p->t_pred, p->scratch_gib, p->max_active, p->n_groups);
     if (r) return r;
     CK(cudaEventRecord(h->ev[9], h->st));
     CK(cudaStreamSynchronize(h->st));

@@ -864,7 +864,7 @@ void oi_launch_pack(const int* indices, long long total, const double* ox, const
 // (number of slots with N > x): every grid below is exact in the slot dimension.  Big batches launch
 // the tile-parallel kernels one block row at a time (exact in both dimensions); small batches (the
 // optimiser's tail) use one 2-D launch to save launch latency.
-#define OI_ROWWISE_MIN_SLOTS 96
+#define OI_ROWWISE_MIN_SLOTS OI_ROWWISE_MIN_SLOTS_HOST
 void oi_launch_build(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, OiCellArrays ca, OiPacked pk, cudaStream_t st) {
     if (A >= OI_ROWWISE_MIN_SLOTS) {
         for (int i = 0; i < Nmax; i++) k_build<<<dim3(i + 1, cnt_gt[i]), 256, 0, st>>>(slots, ca, pk, i);

@@ -4,6 +4,8 @@
 #include "oi_types.h"
 
 #define TILE_PER_THREAD_256 (OI_TILE / 256)
+#define OI_ROWWISE_MIN_SLOTS_HOST 96   // batches at least this big launch the tile-parallel kernels one block row at a time
+#define OI_DEFAULT_GROUPS 4
 #define OI_SMEM_CHOL (2 * OI_NB * 68 * 8 + 4 * 64 * 8)   // T + W of the diagonal factor + per-warp scratch (>= the cp.async pipeline)
 #define OI_SMEM_TRTRI (2 * OI_NB * 68 * 8)    // two resident 64x64 tiles (>= the cp.async pipeline)
 

@@ -99,7 +99,7 @@ class Handle:
         return nlz, grad
 
     def make_params(self, radius_m, t_pred, prior_mean, x0=None, mode=0, grad_convention=0, maxiter=0,
-                    gtol=0.0, scratch_gib=0.0, max_active=0):
+                    gtol=0.0, scratch_gib=0.0, max_active=0, n_groups=0):
         p = _lib.OiParams()
         p.radius_m, p.t_pred, p.prior_mean = float(radius_m), float(t_pred), float(prior_mean)
         x0 = [0.0] * 5 if x0 is None else list(x0)
@@ -108,6 +108,7 @@ class Handle:
             p.x0[i] = float(v)
         p.mode, p.grad_convention, p.maxiter = int(mode), int(grad_convention), int(maxiter)
         p.gtol, p.scratch_gib, p.max_active = float(gtol), float(scratch_gib), int(max_active)
+        p.n_groups = int(n_groups)
         return p
 
     def run(self, params, hypers_in=None):
