@@ -39,6 +39,11 @@ enum { OI_OK = 0, OI_ERR_ARG = -1, OI_ERR_CUDA = -2, OI_ERR_STATE = -3, OI_ERR_N
 /* mode */
 enum { OI_MODE_FIT = 0,      /* GPR3D(index, opt=True):  fit by CG then predict  */
        OI_MODE_PREDICT = 1   /* GPR3D(index, opt=False): predict with hypers_in   */ };
+/* execution engine.  LOCKSTEP (default): one launch per algorithmic step over all active cells, n_groups
+ * independent groups on their own streams.  PERSISTENT: one resident kernel, groups of CTAs walk cells through
+ * whole evaluations + optimiser steps (measured slower on the day workload; kept as an option).
+ * Both run the same tile code and give bit-identical results. */
+enum { OI_ENGINE_LOCKSTEP = 0, OI_ENGINE_PERSISTENT = 1 };
 /* gradient convention of SMLII: the reference's components 3 and 4 are twice the true derivative
  * (GPR_CS2S3.py:135-138).  REFERENCE reproduces that; EXACT gives the true gradient. */
 enum { OI_GRAD_REFERENCE = 0, OI_GRAD_EXACT = 1 };
@@ -58,7 +63,11 @@ typedef struct oi_params {
     double gtol;            /* 0 => 1e-5 (scipy default)                                                */
     double scratch_gib;     /* device scratch budget for the lockstep batch, 0 => automatic             */
     int32_t max_active;     /* maximum cells evaluated per lockstep iteration, 0 => automatic           */
-    int32_t n_groups;       /* independent lockstep groups (one CUDA stream each) whose kernels overlap, 0 => automatic */
+    int32_t n_groups;       /* lockstep engine: independent groups (one CUDA stream each) whose kernels overlap, 0 => automatic */
+    int32_t engine;         /* OI_ENGINE_*                                                                */
+    int32_t group_size;     /* persistent engine: CTAs that share one cell, 0 => automatic (4, growing in the tail) */
+    int32_t evals_per_launch; /* persistent engine: evaluations a cell advances per launch, 0 => 128      */
+    int32_t reserved;
 } oi_params;
 
 typedef struct oi_stats {
@@ -74,10 +83,17 @@ typedef struct oi_stats {
     double ms_build, ms_chol, ms_fwd, ms_trtri, ms_alpha, ms_lauum, ms_finalize;  /* per kernel family   */
     double flops_chol, flops_trtri, flops_lauum;   /* n^3/3 each per evaluation            */
     int64_t launches_chol, launches_trtri, launches_lauum;
-    int64_t n_groups;       /* lockstep groups used; with > 1 the per-family ms_* are per-stream times that overlap */
+    int64_t n_groups;       /* groups used (last launch); lockstep engine with > 1: the per-family ms_* are per-stream times that overlap */
+    int64_t group_size;     /* persistent engine: CTAs per group of the last launch                      */
+    int64_t launches_persistent;
+    double ms_persistent;   /* device time inside k_gp_persistent (CUDA events)                          */
+    double cycles_phase[8]; /* persistent engine: CTA clock cycles per phase summed over CTAs:
+                               build, chol, scale, fwd+trtri, alpha, lauum+trace, finalize, idle/queue   */
 } oi_stats;
 
 int  oi_version(void);
+int  oi_sizeof_params(void);   /* sizeof(oi_params) / sizeof(oi_stats) of the built library (binding self-check) */
+int  oi_sizeof_stats(void);
 const char* oi_last_error(void);
 
 int  oi_create(int device, oi_handle** out);

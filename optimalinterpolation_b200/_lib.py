@@ -11,14 +11,15 @@ LIB_PATH = os.path.join(_HERE, "csrc", "liboi_b200.so")
 
 EXPORTS = ("oi_version", "oi_last_error", "oi_create", "oi_destroy", "oi_set_observations", "oi_set_cells",
            "oi_gather_neighbours", "oi_get_neighbours", "oi_nlml_grad", "oi_run", "oi_get_results",
-           "oi_get_stats", "oi_gpr_day", "oi_set_stream")
+           "oi_get_stats", "oi_gpr_day", "oi_set_stream", "oi_sizeof_params", "oi_sizeof_stats")
 
 
 class OiParams(C.Structure):
     _fields_ = [("radius_m", C.c_double), ("t_pred", C.c_double), ("prior_mean", C.c_double),
                 ("n_hyp", C.c_int32), ("mode", C.c_int32), ("grad_convention", C.c_int32), ("maxiter", C.c_int32),
                 ("x0", C.c_double * 6), ("gtol", C.c_double), ("scratch_gib", C.c_double),
-                ("max_active", C.c_int32), ("n_groups", C.c_int32)]
+                ("max_active", C.c_int32), ("n_groups", C.c_int32), ("engine", C.c_int32), ("group_size", C.c_int32),
+                ("evals_per_launch", C.c_int32), ("reserved", C.c_int32)]
 
 
 class OiStats(C.Structure):
@@ -29,7 +30,8 @@ class OiStats(C.Structure):
                 ("ms_alpha", C.c_double), ("ms_lauum", C.c_double), ("ms_finalize", C.c_double),
                 ("flops_chol", C.c_double), ("flops_trtri", C.c_double), ("flops_lauum", C.c_double),
                 ("launches_chol", C.c_int64), ("launches_trtri", C.c_int64), ("launches_lauum", C.c_int64),
-                ("n_groups", C.c_int64)]
+                ("n_groups", C.c_int64), ("group_size", C.c_int64), ("launches_persistent", C.c_int64),
+                ("ms_persistent", C.c_double), ("cycles_phase", C.c_double * 8)]
 
 
 _lib = None
@@ -70,5 +72,9 @@ def load():
     L.oi_get_results.argtypes = [vp, dp, ip, ip, ip]
     L.oi_get_stats.argtypes = [vp, C.POINTER(OiStats)]
     L.oi_gpr_day.argtypes = [vp, dp, dp, dp, dp, C.c_int64, dp, C.c_int64, C.POINTER(OiParams), dp, dp, ip, ip, ip]
+    L.oi_sizeof_params.restype = C.c_int
+    L.oi_sizeof_stats.restype = C.c_int
+    if L.oi_sizeof_params() != C.sizeof(OiParams) or L.oi_sizeof_stats() != C.sizeof(OiStats):
+        raise RuntimeError("liboi_b200.so does not match this binding (struct sizes differ): rebuild the library")
     _lib = L
     return L

@@ -51,6 +51,11 @@ struct oi_handle {
     int slot_cap = 0;
     cudaEvent_t ev[10]{};
     std::vector<struct OiGroup*> groups;
+    // persistent engine
+    OiWork* d_work = nullptr; OiWork* h_work = nullptr; int work_cap = 0;
+    OiGroupCtl* d_ctl = nullptr; int* d_pfail = nullptr; int* d_queue = nullptr; OiPersistAcc* d_acc = nullptr; int ctl_cap = 0;
+    int* h_phase_pinned = nullptr; int64_t phase_cap = 0;
+    int persist_capacity = 0;
     oi_stats stats{};
     bool have_results = false;
 };
@@ -68,7 +73,9 @@ static size_t slot_bytes(int n) {
     return b;
 }
 
-extern "C" int oi_version(void) { return 100; }
+extern "C" int oi_version(void) { return 110; }
+extern "C" int oi_sizeof_params(void) { return (int)sizeof(oi_params); }
+extern "C" int oi_sizeof_stats(void) { return (int)sizeof(oi_stats); }
 extern "C" const char* oi_last_error(void) { return g_err.c_str(); }
 
 extern "C" int oi_create(int device, oi_handle** out) {
@@ -118,6 +125,8 @@ extern "C" void oi_destroy(oi_handle* h) {
     cudaFree(h->arena); cudaFree(h->d_slots); cudaFree(h->d_slot_phase); cudaFree(h->d_fail);
     cudaFreeHost(h->h_slots); cudaFreeHost(h->h_slot_phase);
     free_groups(h);
+    cudaFree(h->d_work); cudaFreeHost(h->h_work); cudaFree(h->d_ctl); cudaFree(h->d_pfail); cudaFree(h->d_queue); cudaFree(h->d_acc);
+    cudaFreeHost(h->h_phase_pinned);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->own_st) cudaStreamDestroy(h->own_st);
     delete h;
@@ -457,6 +466,122 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
     return rc2;
 }
 
+// ------------------------------------------------------------------------------------------
+// the persistent group engine (k_gp_persistent): the host only builds the work list of unfinished
+// cells (largest first), launches the resident grid and reads the phases back; a launch lets every
+// cell advance by up to evals_cap evaluations.  The group size grows when few cells are left so that
+// the optimiser's tail still uses the whole GPU.
+// ------------------------------------------------------------------------------------------
+static int run_persistent(oi_handle* h, std::vector<int>& h_phase, const OiRunConst& rc, double t_pred,
+                          double scratch_gib, int group_size, int evals_cap) {
+    const int nc = (int)h->n_cells;
+    std::vector<int> pending;
+    pending.reserve(nc);
+    for (int c = 0; c < nc; c++)
+        if (h->h_counts[c] > 0 && h_phase[c] != OI_PH_DONE) pending.push_back(c);
+    std::stable_sort(pending.begin(), pending.end(), [&](int a, int b) { return h->h_counts[a] > h->h_counts[b]; });
+    if (pending.empty()) return OI_OK;
+    if (const char* e = std::getenv("OI_GROUP_SIZE")) group_size = std::atoi(e);
+    if (const char* e = std::getenv("OI_EVALS_CAP")) evals_cap = std::atoi(e);
+    if (evals_cap <= 0) evals_cap = 128;
+    if (!h->persist_capacity) h->persist_capacity = oi_persistent_capacity();
+    const int cap = h->persist_capacity;
+    if (cap <= 0) return fail(OI_ERR_CUDA, "run_persistent: the persistent kernel does not fit on this device");
+    if ((int)pending.size() > h->work_cap) {
+        cudaFree(h->d_work); cudaFreeHost(h->h_work);
+        CK(cudaMalloc(&h->d_work, pending.size() * sizeof(OiWork)));
+        CK(cudaMallocHost(&h->h_work, pending.size() * sizeof(OiWork)));
+        h->work_cap = (int)pending.size();
+    }
+    if (cap > h->ctl_cap) {
+        cudaFree(h->d_ctl); cudaFree(h->d_pfail); cudaFree(h->d_queue); cudaFree(h->d_acc);
+        CK(cudaMalloc(&h->d_ctl, (size_t)cap * sizeof(OiGroupCtl))); CK(cudaMalloc(&h->d_pfail, (size_t)cap * 4));
+        CK(cudaMalloc(&h->d_queue, 4)); CK(cudaMalloc(&h->d_acc, sizeof(OiPersistAcc)));
+        h->ctl_cap = cap;
+    }
+    if (nc > h->phase_cap) {
+        cudaFreeHost(h->h_phase_pinned);
+        CK(cudaMallocHost(&h->h_phase_pinned, (size_t)nc * 4));
+        h->phase_cap = nc;
+    }
+    size_t budget;
+    if (scratch_gib > 0) budget = (size_t)(scratch_gib * 1073741824.0);
+    else {
+        size_t fr = 0, tot = 0;
+        CK(cudaMemGetInfo(&fr, &tot));
+        budget = std::min<size_t>((size_t)((fr + h->arena_bytes) * 0.8), (size_t)64 << 30);
+    }
+    FILE* trace = nullptr;
+    if (const char* tp = std::getenv("OI_TRACE")) {
+        trace = std::fopen(tp, "a");
+        if (trace) std::fprintf(trace, "launch,cells,group_size,groups,ms,evals,pred,flops_factor,cyc_build,cyc_chol,cyc_scale,cyc_fwd_trtri,cyc_alpha,cyc_lauum,cyc_final,cyc_idle\n");
+    }
+    OiPacked pk{h->px, h->py, h->pt, h->pr};
+    int rcode = OI_OK;
+    while (!pending.empty()) {
+        const int R = (int)pending.size();
+        int gs = group_size > 0 ? group_size : OI_DEFAULT_GROUP_SIZE;
+        while (gs < 32 && (long long)R * gs * 2 <= cap) gs *= 2;       // few cells left: bigger groups
+        gs = std::max(1, std::min(gs, cap));
+        const size_t stride = align_up(slot_bytes(h->h_counts[pending[0]]), 256);
+        int n_groups = std::min(cap / gs, R);
+        n_groups = (int)std::min<size_t>((size_t)n_groups, std::max<size_t>(budget / stride, 1));
+        if (stride * n_groups > h->arena_bytes) {
+            cudaFree(h->arena); h->arena = nullptr; h->arena_bytes = 0;
+            cudaError_t e = cudaMalloc(&h->arena, stride * n_groups);
+            if (e != cudaSuccess) { rcode = fail(OI_ERR_NOMEM, std::string("run_persistent: scratch: ") + cudaGetErrorString(e)); break; }
+            h->arena_bytes = stride * n_groups;
+        }
+        for (int q = 0; q < R; q++) { int c = pending[q]; h->h_work[q] = OiWork{h->h_offsets[c], c, h->h_counts[c]}; }
+        cudaStream_t st = h->st;
+        CK(cudaMemcpyAsync(h->d_work, h->h_work, (size_t)R * sizeof(OiWork), cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(h->d_ctl, 0, (size_t)n_groups * sizeof(OiGroupCtl), st));
+        CK(cudaMemsetAsync(h->d_queue, 0, 4, st));
+        CK(cudaMemsetAsync(h->d_acc, 0, sizeof(OiPersistAcc), st));
+        OiPersist P{};
+        P.work = h->d_work; P.n_work = R; P.queue_head = h->d_queue; P.ctl = h->d_ctl; P.scratch = h->arena; P.scratch_stride = stride;
+        P.fail = h->d_pfail; P.gs = gs; P.evals_cap = evals_cap; P.acc = h->d_acc;
+        CK(cudaEventRecord(h->ev[0], st));
+        oi_launch_persistent(P, n_groups, h->ca, pk, rc, t_pred, st);
+        CK(cudaEventRecord(h->ev[1], st));
+        CK(cudaGetLastError());
+        OiPersistAcc acc;
+        CK(cudaMemcpyAsync(h->h_phase_pinned, h->ca.phase, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&acc, h->d_acc, sizeof(acc), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+        oi_stats& S = h->stats;
+        S.ms_factor += ms; S.ms_persistent += ms;
+        S.flops += acc.flops; S.flops_factor += acc.flops_factor; S.flops_chol += acc.flops_chol;
+        // evaluations contribute n^3/3 to each of chol/trtri/lauum, predictions only to chol
+        S.flops_trtri += (acc.flops_factor - acc.flops_chol) / 2; S.flops_lauum += (acc.flops_factor - acc.flops_chol) / 2;
+        S.n_evals += (int64_t)acc.n_evals; S.n_launches += 1; S.n_iterations += 1; S.launches_persistent += 1;
+        double cyc_tot = 0;
+        for (int q = 0; q < 8; q++) { S.cycles_phase[q] += (double)acc.cycles[q]; cyc_tot += (double)acc.cycles[q]; }
+        if (trace) {
+            std::fprintf(trace, "%lld,%d,%d,%d,%.3f,%llu,%llu,%.6g", (long long)S.launches_persistent, R, gs, n_groups, ms,
+                         acc.n_evals, acc.n_pred, acc.flops_factor);
+            for (int q = 0; q < 8; q++) std::fprintf(trace, ",%.4f", cyc_tot > 0 ? (double)acc.cycles[q] / cyc_tot : 0.0);
+            std::fprintf(trace, "\n");
+        }
+        size_t w = 0;
+        for (int q = 0; q < R; q++) {
+            int c = pending[q];
+            h_phase[c] = h->h_phase_pinned[c];
+            if (h_phase[c] != OI_PH_DONE) pending[w++] = c;
+        }
+        pending.resize(w);
+        S.n_groups = n_groups; S.group_size = gs;
+    }
+    if (trace) std::fclose(trace);
+    return rcode;
+}
+
+static int engine_from_env(int engine) {
+    if (const char* e = std::getenv("OI_ENGINE")) engine = std::atoi(e);
+    return engine == OI_ENGINE_PERSISTENT ? OI_ENGINE_PERSISTENT : OI_ENGINE_LOCKSTEP;
+}
+
 static int pack_points(oi_handle* h, double mean) {
     oi_launch_pack(h->indices, h->total, h->ox, h->oy, h->ot, h->oz, mean, h->px, h->py, h->pt, h->pr, h->st);
     CK(cudaGetLastError());
@@ -489,7 +614,8 @@ extern "C" int oi_nlml_grad(oi_handle* h, const double* hypers, int32_t n_hyp, d
     OiRunConst rc{};
     rc.mean = prior_mean; rc.gtol = 1e-5; rc.n_hyp = n_hyp; rc.grad_convention = grad_convention; rc.maxiter = 0;
     reset_stats(h);
-    r = run_lockstep(h, phase, rc, 0.0, 0.0, 0, 0);
+    r = engine_from_env(0) == OI_ENGINE_LOCKSTEP ? run_lockstep(h, phase, rc, 0.0, 0.0, 0, 0)
+                                                    : run_persistent(h, phase, rc, 0.0, 0.0, 0, 0);
     if (r) return r;
     std::vector<double> f(nc), g((size_t)nc * OI_MAXH);
     CK(cudaMemcpy(f.data(), h->ca.evf, (size_t)nc * 8, cudaMemcpyDeviceToHost));
@@ -538,7 +664,9 @@ extern "C" int oi_run(oi_handle* h, const oi_params* p, const double* hypers_in)
         CK(cudaMemcpyAsync(h->ca.hyp, hypers_in, (size_t)nc * 40, cudaMemcpyHostToDevice, h->st));
     }
     CK(cudaStreamSynchronize(h->st));   // staging vectors go out of scope below
-    r = run_lockstep(h, phase, rc, p->t_pred, p->scratch_gib, p->max_active, p->n_groups);
+    r = engine_from_env(p->engine) == OI_ENGINE_LOCKSTEP
+            ? run_lockstep(h, phase, rc, p->t_pred, p->scratch_gib, p->max_active, p->n_groups)
+            : run_persistent(h, phase, rc, p->t_pred, p->scratch_gib, p->group_size, p->evals_per_launch);
     if (r) return r;
     CK(cudaEventRecord(h->ev[9], h->st));
     CK(cudaStreamSynchronize(h->st));

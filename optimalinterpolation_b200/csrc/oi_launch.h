@@ -3,12 +3,18 @@
 #include <cuda_runtime.h>
 #include "oi_types.h"
 
-#define TILE_PER_THREAD_256 (OI_TILE / 256)
+#define OI_THREADS 128                 // threads of every tile CTA (4 warps, 2x2 warp tiles of 32x32)
 #define OI_ROWWISE_MIN_SLOTS_HOST 96   // batches at least this big launch the tile-parallel kernels one block row at a time
-#define OI_DEFAULT_GROUPS 4
-#define OI_SMEM_CHOL (2 * OI_NB * 68 * 8 + 4 * 64 * 8)   // T + W of the diagonal factor + per-warp scratch (>= the cp.async pipeline)
-#define OI_SMEM_TRTRI (2 * OI_NB * 68 * 8)    // two resident 64x64 tiles (>= the cp.async pipeline)
+#define OI_DEFAULT_GROUPS 8
+#define OI_DEFAULT_GROUP_SIZE 4        // CTAs per group of the persistent engine while cells are plentiful
+#define OI_SMEM_BYTES (2 * OI_NB * 68 * 8 + 4 * 64 * 8 + 16)   // T + W of the diagonal factor + per-warp scratch + flag (>= the cp.async pipeline)
+#define OI_SMEM_PIPE (3 * 2 * OI_NB * 20 * 8)                  // 3-stage cp.async pipeline of two 64x16 operand chunks
 
+struct OiRunConst {
+    double mean, gtol;
+    int n_hyp, grad_convention, maxiter;
+    double x0[6];
+};
 void oi_launch_count(const double* ox, const double* oy, int n_obs, const double* X, int n_cells, double r2, int* counts,
                      cudaStream_t st);
 void oi_launch_scan(const int* counts, int n, long long* offsets, cudaStream_t st);
@@ -25,11 +31,7 @@ void oi_launch_trtri(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, in
 void oi_launch_alpha(const OiSlot* slots, int A, int Nmax, const int* phase, cudaStream_t st);
 void oi_launch_lauum_trace(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, OiCellArrays ca, OiPacked pk, cudaStream_t st);
 
-// oi_optim.cu
-struct OiRunConst {
-    double mean, gtol;
-    int n_hyp, grad_convention, maxiter;
-    double x0[6];
-};
+void oi_launch_persistent(const OiPersist& P, int n_groups, OiCellArrays ca, OiPacked pk, OiRunConst rc, double t_pred, cudaStream_t st);
+int oi_persistent_capacity();   // co-resident CTAs of the persistent kernel on the current device
 void oi_launch_cg_init(OiCellArrays ca, int n_cells, OiRunConst rc, cudaStream_t st);
 void oi_launch_finalize(const OiSlot* slots, int A, OiCellArrays ca, OiRunConst rc, int* slot_phase, cudaStream_t st);

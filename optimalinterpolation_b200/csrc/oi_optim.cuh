@@ -1,9 +1,11 @@
-// Finalisation of one lockstep evaluation + the per-cell optimiser step (compiled with -fmad=false
-// so the optimiser's arithmetic rounds like the NumPy/Python code it restates, cg_scipy.h).
+// Finalisation of one evaluation + the per-cell optimiser step, executed by ONE WARP per cell (the
+// translation unit is compiled with -fmad=false so the optimiser's arithmetic rounds like the
+// NumPy/Python code it restates, cg_scipy.h).
 //
 //   FIT / EVAL : nlZ and gradient as SMLII returns them (GPR_CS2S3.py:128-140), then one resume of the
 //                scipy-CG state machine (GPR_CS2S3.py:166) -> next trial hyperparameters or "converged"
 //   PREDICT    : fs, sfs2, lZ and the hyperparameters as GPR3D returns them (GPR_CS2S3.py:179-191)
+#pragma once
 #include <cuda_runtime.h>
 #include <math.h>
 #include "oi_types.h"
@@ -24,28 +26,25 @@ __global__ void k_cg_init(OiCellArrays ca, int n_cells, OiRunConst rc) {
     for (int q = 0; q < 5; q++) ca.hyp[5 * (size_t)c + q] = exp(L.req_x[q]);
 }
 
-__global__ void __launch_bounds__(128) k_finalize(const OiSlot* __restrict__ slots, int A, OiCellArrays ca, OiRunConst rc,
-                                                  int* __restrict__ slot_phase) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= A) return;
-    const OiSlot s = slots[warp];
-    const int phase = ca.phase[s.cell];
-    const bool failed = *s.fail != 0;
+// Returns the cell's new phase (valid in lane 0; broadcast by the caller if needed).  All loads of data
+// produced by other CTAs go through L2 (__ldcg), see oi_tiles.cuh.
+__device__ __noinline__ int warp_finalize(const OiSlot s, const OiCellArrays ca, const OiRunConst rc, int phase, int lane) {
+    const bool failed = *(volatile int*)s.fail != 0;
     double S[5] = {0, 0, 0, 0, 0};
     if (!failed && phase != OI_PH_PREDICT) {
         const int nt = s.N * (s.N + 1) / 2;
         const double* tp = s.part + s.N + 8;
         for (int t = lane; t < nt; t += 32)
-            for (int q = 0; q < 5; q++) S[q] += tp[5 * (size_t)t + q];
+            for (int q = 0; q < 5; q++) S[q] += __ldcg(&tp[5 * (size_t)t + q]);
         for (int q = 0; q < 5; q++)
             for (int o = 16; o > 0; o >>= 1) S[q] += __shfl_down_sync(0xffffffffu, S[q], o);
     }
-    if (lane != 0) return;
+    if (lane != 0) return OI_PH_DONE;
     double logdet = 0.0;
-    if (!failed) for (int k = 0; k < s.N; k++) logdet += s.part[k];
-    const double quad = s.part[s.N + 0], vt = s.part[s.N + 1], vv = s.part[s.N + 2];
+    if (!failed) for (int k = 0; k < s.N; k++) logdet += __ldcg(&s.part[k]);
+    const double quad = __ldcg(&s.part[s.N + 0]), vt = __ldcg(&s.part[s.N + 1]), vv = __ldcg(&s.part[s.N + 2]);
     double* h = ca.hyp + 5 * (size_t)s.cell;
-    const double sf2 = h[3], sn2 = h[4];
+    const double sf2 = __ldcg(&h[3]), sn2 = __ldcg(&h[4]);
     int newphase = OI_PH_DONE;
     if (phase == OI_PH_PREDICT) {
         double* o = ca.out + 8 * (size_t)s.cell;
@@ -56,7 +55,7 @@ __global__ void __launch_bounds__(128) k_finalize(const OiSlot* __restrict__ slo
             o[0] = rc.mean + vt;                                   // fs  = mean + k*^T A            (:181)
             o[1] = sqrt(sf2 - vv);                                 // sfs2 = sqrt(k** - v^T v)       (:182)
             o[2] = -quad / 2 - logdet - s.n * LOG_2PI / 2;         // lZ                             (:179)
-            for (int q = 0; q < 5; q++) o[3 + q] = h[q];
+            for (int q = 0; q < 5; q++) o[3 + q] = __ldcg(&h[q]);
         }
     } else {
         double f, g[OI_MAXH];
@@ -91,12 +90,5 @@ __global__ void __launch_bounds__(128) k_finalize(const OiSlot* __restrict__ slo
         }
     }
     ca.phase[s.cell] = newphase;
-    slot_phase[warp] = newphase;
-}
-
-void oi_launch_cg_init(OiCellArrays ca, int n_cells, OiRunConst rc, cudaStream_t st) {
-    k_cg_init<<<(n_cells + 127) / 128, 128, 0, st>>>(ca, n_cells, rc);
-}
-void oi_launch_finalize(const OiSlot* slots, int A, OiCellArrays ca, OiRunConst rc, int* slot_phase, cudaStream_t st) {
-    k_finalize<<<(A * 32 + 127) / 128, 128, 0, st>>>(slots, A, ca, rc, slot_phase);
+    return newphase;
 }

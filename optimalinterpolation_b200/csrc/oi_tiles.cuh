@@ -1,0 +1,742 @@
+// Tile-level device functions of the per-cell GP hot path.  Every function is executed
+// by ONE CTA of OI_THREADS (128) threads on one 64x64 tile (or one cell for the substitutions) and is shared
+// by the two execution engines:
+//   * the persistent group kernel  (oi_persist.cu): a group of CTAs walks one cell through a whole
+//     NLML+gradient evaluation, synchronising through a global-memory group barrier;
+//   * the lockstep launch-per-step kernels (oi_kernels.cu): one launch per algorithmic step over all cells.
+// Both engines therefore produce bit-identical numbers (fixed reduction orders, no atomics on data).
+// The translation unit is compiled with -fmad=false (the optimiser restatement needs NumPy's rounding);
+// the multiply-adds of the hot scalar loops are therefore written as explicit fma().
+//
+//   tile_build                  Matern-3/2 ARD covariance   (GPR_CS2S3.py:78-105, :126)
+//   tile_chol_update / _panel   blocked left-looking Cholesky, FP64 DMMA tiles (np.linalg.cholesky, :126/:177)
+//   tile_scale                  Ls_ij = L_ii^-1 L_ij
+//   cell_fwd                    t = L^-1 (y - m), v = L^-1 k*   (:127, :178-180)
+//   tile_trtri                  U = L^-T by block distance, FP64 DMMA tiles      (explicit inverse of :130)
+//   rows_alpha                  alpha = U t
+//   tile_lauum_trace            K^-1 tiles = U U^T fused with the five trace terms of :131-138,
+//                               dK/dtheta recomputed in registers, K^-1 never written
+//
+// All dense contractions are NT GEMM tiles (both operands K-contiguous) on mma.sync.m8n8k4.f64
+// (SASS DMMA.8x8x4), fed by a 3-stage cp.async pipeline; tcgen05 has no FP64 kind.
+//
+// Memory-model rule (persistent engine): data written by one CTA and read by another inside the same
+// launch must not be served from a stale L1 line, so every load of MUTABLE global data goes through
+// L2: cp.async.cg, __ldcg or volatile.  Immutable inputs (packed coordinates, slot table) use plain loads.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "oi_types.h"
+#include "oi_launch.h"
+
+#define NB OI_NB
+#define KT 16
+#define LDS_ (KT + 4)          // smem row stride (doubles) of a streamed operand chunk: conflict-free DMMA fragment loads
+#define STAGES 3
+#define GEMM_THREADS OI_THREADS
+#define TS 68                  // smem row stride of a resident 64x64 tile
+#define STAGE_DOUBLES (2 * NB * LDS_)
+#define PIPE_BYTES (STAGES * STAGE_DOUBLES * 8)
+
+#define ROOT3 1.7320508075688772   // np.sqrt(3.)
+#define OI_FAILED(s) (*(volatile int*)(s).fail != 0)
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void tile_ij(int t, int& i, int& j) {
+    // lower-triangular tile enumeration t -> (i, j), j <= i, row by row
+    int r = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((r + 1) * (r + 2) / 2 <= t) r++;
+    while (r * (r + 1) / 2 > t) r--;
+    i = r; j = t - r * (r + 1) / 2;
+}
+
+// Matern-3/2 pair quantities exactly in the reference's operation order (no FMA contraction):
+// Q = sqrt(((dx*dx) + dy*dy) + dt*dt) of pre-scaled coordinates (scipy pdist 'euclidean').
+__device__ __forceinline__ double pair_Q(double dx, double dy, double dt) {
+    double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dt, dt));
+    return sqrt(s);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel (2): covariance tile.  K = sf2*(1+Q)exp(-Q) + sn2*I on the lower block triangle
+// (GPR_CS2S3.py:93-94, :126); padding rows/cols are identity so every later tile is full.
+// smem: 6*NB doubles.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_build(const OiSlot& s, const OiCellArrays& ca, const OiPacked& pk, int i, int j, double* smem) {
+    const int tid = threadIdx.x;
+    if (i == 0 && tid == 0) *s.fail = 0;
+    double(*ru)[NB] = (double(*)[NB])smem;
+    double(*cu)[NB] = ru + 3;
+    const double* h = ca.hyp + 5 * (size_t)s.cell;
+    const double h0 = __ldcg(h + 0), h1 = __ldcg(h + 1), h2 = __ldcg(h + 2), sf2 = __ldcg(h + 3), sn2 = __ldcg(h + 4);
+    __syncthreads();
+    {
+        int which = tid / NB, q = tid % NB;
+        int g = (which ? j : i) * NB + q;
+        double ux = 0, uy = 0, ut = 0;
+        if (g < s.n) {
+            // np.sqrt(3.)*x/ell  (GPR_CS2S3.py:93): multiply, then divide
+            ux = (ROOT3 * pk.x[s.pt_off + g]) / h0;
+            uy = (ROOT3 * pk.y[s.pt_off + g]) / h1;
+            ut = (ROOT3 * pk.t[s.pt_off + g]) / h2;
+        }
+        double(*dst)[NB] = which ? cu : ru;
+        dst[0][q] = ux; dst[1][q] = uy; dst[2][q] = ut;
+    }
+    __syncthreads();
+    const long long ld = s.npad;
+#pragma unroll 4
+    for (int e = 0; e < OI_TILE / OI_THREADS; e++) {
+        int idx = tid + e * OI_THREADS;
+        int r = idx / NB, c = idx % NB;
+        int gi = i * NB + r, gj = j * NB + c;
+        double val;
+        if (gi >= s.n || gj >= s.n) val = (gi == gj) ? 1.0 : 0.0;
+        else if (gi == gj) val = sf2 + sn2;
+        else {
+            double Q = pair_Q(ru[0][r] - cu[0][c], ru[1][r] - cu[1][c], ru[2][r] - cu[2][c]);
+            // + np.eye(n)*sn2 off the diagonal is +0*sn2: NaN when sn2 overflowed (GPR_CS2S3.py:126)
+            val = sf2 * ((1.0 + Q) * exp(-Q)) + 0.0 * sn2;
+        }
+        s.M[(long long)gi * ld + gj] = val;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// FP64 DMMA tile core: acc(64x64) += A(64 x [k0,k1)) * B(64 x [k0,k1))^T, both K-contiguous.
+// 4 warps (2x2), warp tile 32x32 = 4x4 m8n8k4 tiles, 3-stage cp.async pipeline of 16-wide chunks.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_stage(double* st, const double* __restrict__ A, long long lda,
+                                           const double* __restrict__ B, long long ldb, int kk, int tid) {
+    double* As = st;
+    double* Bs = st + NB * LDS_;
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+        int c = tid + it * GEMM_THREADS;      // 0..511
+        int row = c >> 3, col = (c & 7) * 2;
+        cp_async16(&As[row * LDS_ + col], &A[(long long)row * lda + kk + col]);
+        cp_async16(&Bs[row * LDS_ + col], &B[(long long)row * ldb + kk + col]);
+    }
+}
+
+// Sub-tile ranges: a warp computes the 8x8 sub-tiles mb in [mlo, mhi) x nb in [nlo, nhi) of its 32x32
+// warp tile for one K chunk.  All bounds are in {0, 2, 4} (structure comes in multiples of 16), so each
+// combination is its own fully unrolled code path; ranges are warp-uniform.  They skip structural zeros
+// (triangular diagonal blocks), the unused half of diagonal tiles and the rows/cols beyond the cell's real
+// size in its last block.
+struct SubRange { int mlo, mhi, nlo, nhi; };
+__device__ __forceinline__ int clamp024(int v) { return v <= 0 ? 0 : (v >= 32 ? 4 : (v >= 16 ? 2 : 0)); }
+// sub-tiles whose first row (col) is < limit / whose last row (col) is >= limit, limit a multiple of 16
+__device__ __forceinline__ int hi_lt(int w, int limit) { return clamp024(limit - w * 32); }
+__device__ __forceinline__ int lo_ge(int w, int limit) { return clamp024(limit - w * 32); }
+
+template <int MLO, int MHI, int NLO, int NHI>
+__device__ __forceinline__ void mma_chunk_t(double (&acc)[4][4][2], const double* As, const double* Bs, int lda_s, int ldb_s,
+                                            int wm, int wn, int lane, int kofs, int ksteps) {
+    const int fr = lane >> 2, fc = lane & 3;
+#pragma unroll
+    for (int ks = 0; ks < ksteps; ks++) {
+        double a[4], b[4];
+#pragma unroll
+        for (int mb = MLO; mb < MHI; mb++) a[mb] = As[(wm * 32 + mb * 8 + fr) * lda_s + kofs + ks * 4 + fc];
+#pragma unroll
+        for (int nb = NLO; nb < NHI; nb++) b[nb] = Bs[(wn * 32 + nb * 8 + fr) * ldb_s + kofs + ks * 4 + fc];
+#pragma unroll
+        for (int mb = MLO; mb < MHI; mb++)
+#pragma unroll
+            for (int nb = NLO; nb < NHI; nb++) dmma(acc[mb][nb], a[mb], b[nb]);
+    }
+}
+template <int MLO, int MHI>
+__device__ __forceinline__ void mma_chunk_n(double (&acc)[4][4][2], const double* As, const double* Bs, int lda_s, int ldb_s,
+                                            int wm, int wn, int lane, int kofs, int ksteps, int nlo, int nhi) {
+    if (nlo == 0 && nhi == 4) mma_chunk_t<MLO, MHI, 0, 4>(acc, As, Bs, lda_s, ldb_s, wm, wn, lane, kofs, ksteps);
+    else if (nlo == 0 && nhi == 2) mma_chunk_t<MLO, MHI, 0, 2>(acc, As, Bs, lda_s, ldb_s, wm, wn, lane, kofs, ksteps);
+    else if (nlo == 2 && nhi == 4) mma_chunk_t<MLO, MHI, 2, 4>(acc, As, Bs, lda_s, ldb_s, wm, wn, lane, kofs, ksteps);
+}
+__device__ __forceinline__ void mma_chunk(double (&acc)[4][4][2], const double* As, const double* Bs, int lda_s, int ldb_s,
+                                          int wm, int wn, int lane, int kofs, int ksteps, SubRange r) {
+    if (r.mlo == 0 && r.mhi == 4) mma_chunk_n<0, 4>(acc, As, Bs, lda_s, ldb_s, wm, wn, lane, kofs, ksteps, r.nlo, r.nhi);
+    else if (r.mlo == 0 && r.mhi == 2) mma_chunk_n<0, 2>(acc, As, Bs, lda_s, ldb_s, wm, wn, lane, kofs, ksteps, r.nlo, r.nhi);
+    else if (r.mlo == 2 && r.mhi == 4) mma_chunk_n<2, 4>(acc, As, Bs, lda_s, ldb_s, wm, wn, lane, kofs, ksteps, r.nlo, r.nhi);
+}
+
+// The pipeline starts with a CTA barrier (the shared-memory buffers may still be in use by the previous tile
+// of a persistent CTA) and ends with one (they are free again on return).
+template <class MaskFn>
+__device__ __forceinline__ void gemm_nt_stream(double (&acc)[4][4][2], const double* __restrict__ A, long long lda,
+                                               const double* __restrict__ B, long long ldb, int k0, int k1,
+                                               double* smem, MaskFn maskfn) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int nk = (k1 - k0) / KT;
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nk) load_stage(smem + s * STAGE_DOUBLES, A, lda, B, ldb, k0 + s * KT, tid);
+        cp_async_commit();
+    }
+    for (int it = 0; it < nk; it++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        int nx = it + STAGES - 1;
+        if (nx < nk) load_stage(smem + (nx % STAGES) * STAGE_DOUBLES, A, lda, B, ldb, k0 + nx * KT, tid);
+        cp_async_commit();
+        const double* st = smem + (it % STAGES) * STAGE_DOUBLES;
+        mma_chunk(acc, st, st + NB * LDS_, LDS_, LDS_, wm, wn, lane, 0, KT / 4, maskfn(k0 + it * KT));
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+}
+
+#define ACC_ZERO(acc)                                                        \
+    _Pragma("unroll") for (int mb_ = 0; mb_ < 4; mb_++)                      \
+    _Pragma("unroll") for (int nb_ = 0; nb_ < 4; nb_++) { acc[mb_][nb_][0] = 0.0; acc[mb_][nb_][1] = 0.0; }
+
+// fragment element (mb, nb, e) of this thread sits at tile row/col:
+#define FRAG_ROW(wm, mb, lane) ((wm) * 32 + (mb) * 8 + ((lane) >> 2))
+#define FRAG_COL(wn, nb, lane) ((wn) * 32 + (nb) * 8 + (((lane) & 3) << 1))
+
+// ------------------------------------------------------------------------------------------
+// 64x64 diagonal block: Cholesky factor (lower, in place in T) and its inverse (W), both in shared
+// memory, on 8x8 sub-blocks: the 8x8 pivot block is factored + inverted by one warp in registers
+// (dpotf2 order of operations; a pivot <= 0 sets *s_bad, a NaN pivot propagates -- OpenBLAS potf2
+// semantics, which is what np.linalg.cholesky runs), every other sub-block operation (panel solve,
+// trailing update, inverse by block distance) is one or two DMMA m8n8k4 per 8x8 block.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void diag_factor_invert(double* T, double* W, double* sc, int* s_bad, int tid) {
+    const int warp = tid >> 5, lane = tid & 31, fr = lane >> 2, fc = lane & 3;
+    for (int j = 0; j < 8; j++) {
+        const int jb = j * 8;
+        if (warp == 0) {
+            const int r = lane & 7;
+            double a[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) a[c] = T[(jb + r) * TS + jb + c];
+            bool bad = false;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+#pragma unroll
+                for (int l = 0; l < c; l++) {
+                    double acl = __shfl_sync(0xffffffffu, a[l], c, 8);      // L[c][l]
+                    if (r >= c) a[c] = fma(-a[l], acl, a[c]);
+                }
+                double piv = __shfl_sync(0xffffffffu, a[c], c, 8);
+                if (piv <= 0.0) bad = true;
+                double sq = sqrt(piv), inv = 1.0 / sq;
+                if (r == c) a[c] = sq;
+                else if (r > c) a[c] *= inv;
+            }
+            if (bad) {
+                if (lane == 0) *s_bad = 1;
+            } else {
+                if (lane < 8) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) if (c <= r) T[(jb + r) * TS + jb + c] = a[c];
+                }
+                __syncwarp();
+                // X = L8^-1, lane b owns column b:  x[rr] = -(sum_{l<rr} L[rr][l] x[l]) / L[rr][rr]
+                const int b = r;
+                double x[8];
+#pragma unroll
+                for (int rr = 0; rr < 8; rr++) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int l = 0; l < rr; l++) sacc = fma(T[(jb + rr) * TS + jb + l], x[l], sacc);
+                    double dinv = 1.0 / T[(jb + rr) * TS + jb + rr];
+                    x[rr] = (rr < b) ? 0.0 : ((rr == b) ? dinv : -sacc * dinv);
+                }
+                if (lane < 8) {
+#pragma unroll
+                    for (int rr = 0; rr < 8; rr++) if (rr >= b) W[(jb + rr) * TS + jb + b] = x[rr];
+                }
+            }
+        }
+        __syncthreads();
+        if (*s_bad) return;
+        // panel: L_ij = A_ij * X_jj^T  (i > j)
+        for (int i = j + 1 + warp; i < 8; i += 4) {
+            double c2[2] = {0.0, 0.0};
+#pragma unroll
+            for (int ks = 0; ks < 2; ks++)
+                dmma(c2, T[(i * 8 + fr) * TS + jb + ks * 4 + fc], W[(jb + fr) * TS + jb + ks * 4 + fc]);
+            __syncwarp();
+            T[(i * 8 + fr) * TS + jb + fc * 2] = c2[0];
+            T[(i * 8 + fr) * TS + jb + fc * 2 + 1] = c2[1];
+        }
+        __syncthreads();
+        // trailing update: A_il -= L_ij L_lj^T  (j < l <= i)
+        const int m = 7 - j, cnt = m * (m + 1) / 2;
+        for (int q = warp; q < cnt; q += 4) {
+            int ii, ll;
+            tile_ij(q, ii, ll);
+            const int i = j + 1 + ii, l = j + 1 + ll;
+            double c2[2];
+            c2[0] = T[(i * 8 + fr) * TS + l * 8 + fc * 2];
+            c2[1] = T[(i * 8 + fr) * TS + l * 8 + fc * 2 + 1];
+#pragma unroll
+            for (int ks = 0; ks < 2; ks++)
+                dmma(c2, -T[(i * 8 + fr) * TS + jb + ks * 4 + fc], T[(l * 8 + fr) * TS + jb + ks * 4 + fc]);
+            T[(i * 8 + fr) * TS + l * 8 + fc * 2] = c2[0];
+            T[(i * 8 + fr) * TS + l * 8 + fc * 2 + 1] = c2[1];
+        }
+        __syncthreads();
+    }
+    // inverse by 8x8 block distance: W_ik = -X_ii * sum_{j=k}^{i-1} L_ij W_jk
+    for (int d = 1; d < 8; d++) {
+        for (int kb = warp; kb + d < 8; kb += 4) {
+            const int i = kb + d;
+            double c1[2] = {0.0, 0.0};
+            for (int jj = kb; jj < i; jj++) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ks++)
+                    dmma(c1, T[(i * 8 + fr) * TS + jj * 8 + ks * 4 + fc], W[(jj * 8 + ks * 4 + fc) * TS + kb * 8 + fr]);
+            }
+            sc[fr * 8 + fc * 2] = c1[0];
+            sc[fr * 8 + fc * 2 + 1] = c1[1];
+            __syncwarp();
+            double c2[2] = {0.0, 0.0};
+#pragma unroll
+            for (int ks = 0; ks < 2; ks++)
+                dmma(c2, W[(i * 8 + fr) * TS + i * 8 + ks * 4 + fc], sc[(ks * 4 + fc) * 8 + fr]);
+            W[(i * 8 + fr) * TS + kb * 8 + fc * 2] = -c2[0];
+            W[(i * 8 + fr) * TS + kb * 8 + fc * 2 + 1] = -c2[1];
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel (3a): left-looking block-column update  A_ik -= sum_{j<k} L_ij L_kj^T  (i >= k);
+// the CTA of the diagonal tile then factors it in shared memory (dpotrf semantics: a pivot
+// <= 0 raises the cell's fail flag), inverts the 64x64 factor and stores
+//   Dinv[k] = L_kk^-1 (row-major)   and   M(k,k) = U_kk = L_kk^-T (upper, zeros below).
+// smem: OI_SMEM_BYTES.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_chol_update(const OiSlot& s, int i, int k, double* smem) {
+    const long long ld = s.npad;
+    double acc[4][4][2];
+    ACC_ZERO(acc);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 1, wn = warp & 1;
+    // the tile being updated is fetched up front so its latency hides behind the K loop
+    double2 cin[4][4];
+    {
+        const double* Cr = s.M + (long long)i * NB * ld + (long long)k * NB;
+#pragma unroll
+        for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++)
+                cin[mb][nb] = __ldcg((const double2*)&Cr[(long long)FRAG_ROW(wm, mb, lane) * ld + FRAG_COL(wn, nb, lane)]);
+    }
+    {
+        // rows of block i / cols of block k beyond the cell's size are padding; of the diagonal tile only
+        // the lower triangle is needed (the warp above the diagonal idles)
+        SubRange sr{0, hi_lt(wm, s.n16 - i * NB), 0, hi_lt(wn, s.n16 - k * NB)};
+        if (i == k && wm < wn) sr.mhi = 0;
+        gemm_nt_stream(acc, s.M + (long long)i * NB * ld, ld, s.M + (long long)k * NB * ld, ld, 0, k * NB, smem,
+                       [sr](int) { return sr; });
+    }
+    double* Cg = s.M + (long long)i * NB * ld + (long long)k * NB;
+    if (i != k) {
+#pragma unroll
+        for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++) {
+                double2 v = cin[mb][nb];
+                v.x -= acc[mb][nb][0]; v.y -= acc[mb][nb][1];
+                *(double2*)&Cg[(long long)FRAG_ROW(wm, mb, lane) * ld + FRAG_COL(wn, nb, lane)] = v;
+            }
+        return;
+    }
+    // ---- diagonal tile: T = A_kk - acc, factor + invert in shared memory ----
+    double* T = smem;                    // [64][TS]  A_kk -> L_kk (lower)
+    double* W = smem + NB * TS;          // [64][TS]  L_kk^-1 (lower, zeros above)
+    double* sc = smem + 2 * NB * TS + warp * 64;   // per-warp 8x8 scratch
+    int* s_bad = (int*)(smem + 2 * NB * TS + 4 * 64);
+#pragma unroll
+    for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) {
+            int r = FRAG_ROW(wm, mb, lane), c = FRAG_COL(wn, nb, lane);
+            T[r * TS + c] = cin[mb][nb].x - acc[mb][nb][0];
+            T[r * TS + c + 1] = cin[mb][nb].y - acc[mb][nb][1];
+        }
+    for (int idx = tid; idx < NB * TS; idx += GEMM_THREADS) W[idx] = 0.0;
+    if (tid == 0) *s_bad = 0;
+    __syncthreads();
+    diag_factor_invert(T, W, sc, s_bad, tid);
+    if (*s_bad) {
+        if (tid == 0) *s.fail = 1;
+        return;
+    }
+    if (warp == 0) {
+        // log-determinant part: sum_i log L_ii of this block (GPR_CS2S3.py:128), fixed order
+        double v = log(T[lane * TS + lane]) + log(T[(lane + 32) * TS + lane + 32]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) s.part[k] = v;
+    }
+    double* Dk = s.Dinv + (long long)k * OI_TILE;
+    for (int idx = tid; idx < OI_TILE; idx += GEMM_THREADS) {
+        int r = idx >> 6, c = idx & 63;
+        Dk[idx] = W[r * TS + c];
+        Cg[(long long)r * ld + c] = (c >= r) ? W[c * TS + r] : 0.0;
+    }
+}
+
+// kernel (3b): panel  L_ik = A_ik * L_kk^-T  (i > k), as an NT tile against Dinv[k].  smem: PIPE_BYTES.
+__device__ __forceinline__ void tile_chol_panel(const OiSlot& s, int i, int k, double* smem) {
+    const long long ld = s.npad;
+    double acc[4][4][2];
+    ACC_ZERO(acc);
+    double* Cg = s.M + (long long)i * NB * ld + (long long)k * NB;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 1, wn = warp & 1;
+    {
+        // Dinv[k][nn][kk] is lower triangular: output column nn only needs kk <= nn
+        const int mhi = hi_lt(wm, s.n16 - i * NB);
+        gemm_nt_stream(acc, Cg, ld, s.Dinv + (long long)k * OI_TILE, NB, 0, NB, smem,
+                       [mhi, wn](int kk) { return SubRange{0, mhi, lo_ge(wn, kk), 4}; });
+    }
+#pragma unroll
+    for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) {
+            double2 v; v.x = acc[mb][nb][0]; v.y = acc[mb][nb][1];
+            *(double2*)&Cg[(long long)FRAG_ROW(wm, mb, lane) * ld + FRAG_COL(wn, nb, lane)] = v;
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel (3c): forward substitution with the factor, one CTA per cell:
+//   t = L^-1 (y - m)            (GPR_CS2S3.py:127 inner solve)
+//   v = L^-1 k*   (predict)     (GPR_CS2S3.py:180)
+// scalars: t.t (=> (y-m)^T alpha), v.t (=> k*^T alpha), v.v
+// Runs with 128 or 256 threads: with 128, thread tid also plays virtual thread tid+128 (8 virtual warps),
+// so every sum has the same order either way.  smem: 2*NB + 24 doubles.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cell_fwd(const OiSlot& s, const OiCellArrays& ca, const OiPacked& pk, double t_pred, bool pred,
+                                         double* smem) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nthr = blockDim.x, nwarp = nthr >> 5, passes = 8 / nwarp;     // 128 threads: 2 passes, 256 threads: 1
+    const int nrhs = pred ? 2 : 1;
+    const long long ld = s.npad;
+    double* tv = s.vec;              // t
+    double* vv = s.vec + s.npad;     // v
+    double(*sb)[NB] = (double(*)[NB])smem;             // [2][NB]
+    double(*red)[8] = (double(*)[8])(smem + 2 * NB);   // [3][8]
+    const double* h = ca.hyp + 5 * (size_t)s.cell;
+    const double h0 = __ldcg(h + 0), h1 = __ldcg(h + 1), h2 = __ldcg(h + 2), h3 = __ldcg(h + 3);
+    __syncthreads();
+    // right-hand sides
+    for (int g = tid; g < s.npad; g += nthr) {
+        double r = 0.0, ks = 0.0;
+        if (g < s.n) {
+            r = pk.r[s.pt_off + g];
+            if (pred) {
+                // cdist(sqrt(3)*x/ell, sqrt(3)*xs/ell) (GPR_CS2S3.py:100-101)
+                double dx = (ROOT3 * pk.x[s.pt_off + g]) / h0 - (ROOT3 * ca.X[2 * (size_t)s.cell]) / h0;
+                double dy = (ROOT3 * pk.y[s.pt_off + g]) / h1 - (ROOT3 * ca.X[2 * (size_t)s.cell + 1]) / h1;
+                double dt = (ROOT3 * pk.t[s.pt_off + g]) / h2 - (ROOT3 * t_pred) / h2;
+                double Q = pair_Q(dx, dy, dt);
+                ks = h3 * ((1.0 + Q) * exp(-Q));
+            }
+        }
+        tv[g] = r; vv[g] = ks;
+    }
+    __syncthreads();
+    for (int k = 0; k < s.N; k++) {
+        const int kc = k * NB;
+        // s[r] = sum_{c<kc} Ls[kc+r][c] * x[c]; virtual warp vw owns rows vw*8 .. vw*8+7
+#pragma unroll 1
+        for (int half = 0; half < passes; half++) {
+            const int vw = warp + nwarp * half;
+            double a0[8], a1[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) { a0[q] = 0.0; a1[q] = 0.0; }
+            const double* Lrow = s.M + (long long)(kc + vw * 8) * ld;
+            for (int c = lane; c < kc; c += 32) {
+                double x0 = __ldcg(&tv[c]), x1 = pred ? __ldcg(&vv[c]) : 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    double l = __ldcg(&Lrow[(long long)q * ld + c]);
+                    a0[q] = fma(l, x0, a0[q]); a1[q] = fma(l, x1, a1[q]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a0[q] += __shfl_down_sync(0xffffffffu, a0[q], o);
+                    a1[q] += __shfl_down_sync(0xffffffffu, a1[q], o);
+                }
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) { sb[0][vw * 8 + q] = a0[q]; sb[1][vw * 8 + q] = a1[q]; }
+            }
+        }
+        // x_k = Dinv[k] * b_k - sum_{c<kc} Ls[kc+r][c] x[c]   (lower-triangular 64x64 mat-vec), thread (rhs, row)
+        double dsum = 0.0;
+        if (tid < NB * nrhs) {
+            int rh = tid / NB, r = tid % NB;
+            const double* D = s.Dinv + (long long)k * OI_TILE + r * NB;
+            const double* bsrc = (rh ? vv : tv) + kc;
+            for (int c = 0; c <= r; c++) dsum = fma(__ldcg(&D[c]), __ldcg(&bsrc[c]), dsum);
+        }
+        __syncthreads();
+        if (tid < NB * nrhs) {
+            int rh = tid / NB, r = tid % NB;
+            (rh ? vv : tv)[kc + r] = dsum - sb[rh][r];
+        }
+        __syncthreads();
+    }
+    // scalars, fixed summation order (256 virtual threads, 8 virtual warps)
+#pragma unroll 1
+    for (int half = 0; half < passes; half++) {
+        double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+        for (int g = tid + nthr * half; g < s.npad; g += 256) {
+            double a = __ldcg(&tv[g]), b = pred ? __ldcg(&vv[g]) : 0.0;
+            q0 = fma(a, a, q0); q1 = fma(a, b, q1); q2 = fma(b, b, q2);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            q0 += __shfl_down_sync(0xffffffffu, q0, o);
+            q1 += __shfl_down_sync(0xffffffffu, q1, o);
+            q2 += __shfl_down_sync(0xffffffffu, q2, o);
+        }
+        if (lane == 0) { red[0][warp + nwarp * half] = q0; red[1][warp + nwarp * half] = q1; red[2][warp + nwarp * half] = q2; }
+    }
+    __syncthreads();
+    if (tid < 3) {
+        double a = 0.0;
+        for (int w = 0; w < 8; w++) a += red[tid][w];
+        s.part[s.N + tid] = a;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel (3c'): row scaling  Ls_ij = L_ii^-1 * L_ij  (i > j), in place.
+// With it the forward substitution and the inverse need no per-step triangular solve:
+//   t_i = L_ii^-1 r_i - sum_{j<i} Ls_ij t_j            W_ik = -sum_{j=k}^{i-1} Ls_ij W_jk
+// smem: 2*NB*TS doubles.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_scale(const OiSlot& s, int i, int j, double* smem) {
+    const long long ld = s.npad;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 1, wn = warp & 1;
+    double* TA = smem;             // Dinv_i [m][kk]
+    double* TB = smem + NB * TS;   // L_ij   [kk][n]
+    const double* Di = s.Dinv + (long long)i * OI_TILE;
+    double* Lg = s.M + (long long)i * NB * ld + (long long)j * NB;
+    __syncthreads();
+    for (int idx = tid; idx < OI_TILE / 2; idx += GEMM_THREADS) {
+        int r = idx >> 5, c = (idx & 31) * 2;
+        cp_async16(&TA[r * TS + c], &Di[r * NB + c]);
+        cp_async16(&TB[r * TS + c], &Lg[(long long)r * ld + c]);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    double acc[4][4][2];
+    ACC_ZERO(acc);
+    const int vi = s.n16 - i * NB;              // valid rows of block i
+    const int fr = lane >> 2, fc = lane & 3;
+    // out[m][n] = sum_kk Dinv_i[m][kk] L_ij[kk][n], Dinv_i lower triangular: row m needs kk <= m
+    for (int c = 0; c < NB && c < vi; c += KT) {
+        const int mlo = lo_ge(wm, c), mhi = hi_lt(wm, vi);
+#pragma unroll
+        for (int ks = 0; ks < KT / 4; ks++) {
+            double a[4], b[4];
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++) a[mb] = TA[(wm * 32 + mb * 8 + fr) * TS + c + ks * 4 + fc];
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++) b[nb] = TB[(c + ks * 4 + fc) * TS + wn * 32 + nb * 8 + fr];
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++)
+                if (mb >= mlo && mb < mhi) {
+#pragma unroll
+                    for (int nb = 0; nb < 4; nb++) dmma(acc[mb][nb], a[mb], b[nb]);
+                }
+        }
+    }
+#pragma unroll
+    for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) {
+            double2 v; v.x = acc[mb][nb][0]; v.y = acc[mb][nb][1];
+            *(double2*)&Lg[(long long)FRAG_ROW(wm, mb, lane) * ld + FRAG_COL(wn, nb, lane)] = v;
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel (3d): U = L^-T by block distance d:  W_ik = -sum_{j=k}^{i-1} Ls_ij W_jk, i = k+d,
+// stored transposed (U[k-block][i-block] = W_ik^T) so every later contraction stays NT.
+// smem: PIPE_BYTES.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_trtri(const OiSlot& s, int kb, int d, double* smem) {
+    const int i = kb + d;
+    const long long ld = s.npad;
+    double acc[4][4][2];
+    ACC_ZERO(acc);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 1, wn = warp & 1;
+    {
+        // first K block is U_kk (upper triangular): column nn of the output only needs kk' >= nn;
+        // rows of block i beyond the cell's size are padding
+        const int mhi = hi_lt(wm, s.n16 - i * NB);
+        const int kfirst = kb * NB;
+        gemm_nt_stream(acc, s.M + (long long)i * NB * ld, ld, s.M + (long long)kb * NB * ld, ld, kb * NB, i * NB, smem,
+                       [mhi, wn, kfirst](int kk) {
+                           int c = kk - kfirst;
+                           return SubRange{0, mhi, 0, c < NB ? hi_lt(wn, c + KT) : 4};
+                       });
+    }
+    // transpose through shared memory, then coalesced stores: U[kb*64+nn][i*64+m] = -acc[m][nn]
+    double* TA = smem;             // [nn][m]
+#pragma unroll
+    for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) {
+            int r = FRAG_ROW(wm, mb, lane), c = FRAG_COL(wn, nb, lane);
+            TA[c * TS + r] = -acc[mb][nb][0];
+            TA[(c + 1) * TS + r] = -acc[mb][nb][1];
+        }
+    __syncthreads();
+    double* Ug = s.M + (long long)kb * NB * ld + (long long)i * NB;
+    for (int idx = tid; idx < OI_TILE / 2; idx += GEMM_THREADS) {
+        int r = idx >> 5, c = (idx & 31) * 2;
+        *(double2*)&Ug[(long long)r * ld + c] = *(const double2*)&TA[r * TS + c];
+    }
+}
+
+// kernel (3e): alpha = K^-1 (y-m) = U t   (rows of U dotted with t), 64 rows per call
+__device__ __forceinline__ void rows_alpha(const OiSlot& s, int rb) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long ld = s.npad;
+    const double* tv = s.vec;
+    double* al = s.vec + 2 * (long long)s.npad;
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+        const int r0 = rb * NB + (warp + 4 * half) * 8;
+        double a[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) a[q] = 0.0;
+        const double* Urow = s.M + (long long)r0 * ld;
+        for (int c = rb * NB + lane; c < s.npad; c += 32) {
+            double x = __ldcg(&tv[c]);
+#pragma unroll
+            for (int q = 0; q < 8; q++) a[q] = fma(__ldcg(&Urow[(long long)q * ld + c]), x, a[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a[q] += __shfl_down_sync(0xffffffffu, a[q], o);
+            if (lane == 0) al[r0 + q] = a[q];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel (4): K^-1 tile (i,j) = sum_{m >= i} U_im U_jm^T on DMMA, fused with the trace terms of
+// GPR_CS2S3.py:130-138:  Qm = K^-1 - alpha alpha^T,
+//   S_theta = sum Qm * q_theta^2 exp(-Q)   (theta = x, y, t)      S_3 = sum Qm * (1+Q) exp(-Q)
+//   S_4 = tr(Qm)
+// dK/dtheta is recomputed from the coordinates in registers; K^-1 is never stored.
+// Each tile writes five partial sums; off-diagonal tiles count twice (symmetry).  smem: PIPE_BYTES.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_lauum_trace(const OiSlot& s, const OiCellArrays& ca, const OiPacked& pk, int i, int j, double* smem) {
+    const long long ld = s.npad;
+    double acc[4][4][2];
+    ACC_ZERO(acc);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 1, wn = warp & 1;
+    const double* h = ca.hyp + 5 * (size_t)s.cell;
+    const double h0 = __ldcg(h + 0), h1 = __ldcg(h + 1), h2 = __ldcg(h + 2);
+    double praw[4] = {0, 0, 0, 0};              // this thread's point (row or col of the tile): x, y, t, alpha
+    {
+        int g = ((tid / NB) ? j : i) * NB + tid % NB;
+        if (g < s.n) {
+            praw[0] = pk.x[s.pt_off + g]; praw[1] = pk.y[s.pt_off + g]; praw[2] = pk.t[s.pt_off + g];
+            praw[3] = __ldcg(&s.vec[2 * (long long)s.npad + g]);
+        }
+    }
+    {
+        // K range ends at the cell's real size (rounded to 16); the first K block is U_ii (upper triangular):
+        // row m only needs kk' >= m (for the diagonal tile likewise column n, and the warp above the diagonal idles)
+        const int mhi0 = (i == j && wm < wn) ? 0 : hi_lt(wm, s.n16 - i * NB), nhi0 = hi_lt(wn, s.n16 - j * NB);
+        const int kfirst = i * NB;
+        const bool diag = (i == j);
+        gemm_nt_stream(acc, s.M + (long long)i * NB * ld, ld, s.M + (long long)j * NB * ld, ld, i * NB, s.n16, smem,
+                       [mhi0, nhi0, wm, wn, kfirst, diag](int kk) {
+                           int c = kk - kfirst;
+                           if (c >= NB) return SubRange{0, mhi0, 0, nhi0};
+                           int mh = min(mhi0, hi_lt(wm, c + KT));
+                           int nh = diag ? min(nhi0, hi_lt(wn, c + KT)) : nhi0;
+                           return SubRange{0, mh, 0, nh};
+                       });
+    }
+    // per-point data of the 64 rows and 64 cols: u (3), v (3), alpha (raw values were fetched before the K loop)
+    double(*P)[7][NB] = (double(*)[7][NB])smem;    // P[0]=rows, P[1]=cols
+    double(*red)[4] = (double(*)[4])(smem + 2 * 7 * NB);   // [5][4]
+    {
+        int which = tid / NB, q = tid % NB;        // 128 threads: rows then cols
+        double x = praw[0], y = praw[1], t = praw[2], a = praw[3];
+        P[which][0][q] = (ROOT3 * x) / h0; P[which][1][q] = (ROOT3 * y) / h1; P[which][2][q] = (ROOT3 * t) / h2;
+        // np.sqrt(3.)*(x[:,theta]/ell[theta])  (GPR_CS2S3.py:97): divide, then multiply
+        P[which][3][q] = ROOT3 * (x / h0); P[which][4][q] = ROOT3 * (y / h1); P[which][5][q] = ROOT3 * (t / h2);
+        P[which][6][q] = a;
+    }
+    __syncthreads();
+    double S[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int mb = 0; mb < 4; mb++) {
+        const int r = FRAG_ROW(wm, mb, lane), gi = i * NB + r;
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int c = FRAG_COL(wn, nb, lane) + e, gj = j * NB + c;
+                if (gi < s.n && gj < s.n && gj <= gi) {
+                    double Qm = fma(-P[0][6][r], P[1][6][c], acc[mb][nb][e]);
+                    if (gi == gj) {
+                        // Q = 0: dK_theta = 0, K = sf2
+                        S[3] += Qm; S[4] += Qm;
+                    } else {
+                        Qm *= 2.0;          // (gi, gj) and (gj, gi): K^-1, alpha alpha^T and dK are symmetric
+                        double Q = pair_Q(P[0][0][r] - P[1][0][c], P[0][1][r] - P[1][1][c], P[0][2][r] - P[1][2][c]);
+                        double E = exp(-Q);
+                        double qx = P[0][3][r] - P[1][3][c], qy = P[0][4][r] - P[1][4][c], qt = P[0][5][r] - P[1][5][c];
+                        S[0] = fma(Qm, qx * qx * E, S[0]);
+                        S[1] = fma(Qm, qy * qy * E, S[1]);
+                        S[2] = fma(Qm, qt * qt * E, S[2]);
+                        S[3] = fma(Qm, (1.0 + Q) * E, S[3]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) S[q] += __shfl_down_sync(0xffffffffu, S[q], o);
+        if (lane == 0) red[q][warp] = S[q];
+    }
+    __syncthreads();
+    if (tid < 5) {
+        double v = ((red[tid][0] + red[tid][1]) + red[tid][2]) + red[tid][3];
+        s.part[s.N + 8 + 5 * (long long)(i * (i + 1) / 2 + j) + tid] = v;
+    }
+}

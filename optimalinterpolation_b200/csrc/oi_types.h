@@ -36,3 +36,22 @@ struct OiCellArrays {
 struct OiPacked {
     const double* x; const double* y; const double* t; const double* r;   // r = z - prior mean
 };
+
+// ---- persistent group engine (oi_kernels.cu: k_gp_persistent) ----
+struct OiWork { long long pt_off; int cell, n; };            // one unfinished cell of the work list (sorted by descending n)
+struct OiGroupCtl { unsigned count; int cur[2]; int pad_[29]; };   // 128 B per group: barrier counter + current work index
+struct OiPersistAcc {
+    unsigned long long cycles[8];      // CTA clock cycles per phase (build, chol, scale, fwd+trtri, alpha, lauum, finalize, idle)
+    double flops, flops_factor, flops_chol;
+    unsigned long long n_evals, n_pred;
+};
+struct OiPersist {
+    const OiWork* work; int n_work;
+    int* queue_head;                   // next work index
+    OiGroupCtl* ctl;                   // [n_groups]
+    char* scratch; size_t scratch_stride;   // per-group scratch (sized for the largest cell of the work list)
+    int* fail;                         // [n_groups]
+    int gs;                            // CTAs per group
+    int evals_cap;                     // evaluations a group spends on one cell before it takes the next
+    OiPersistAcc* acc;
+};

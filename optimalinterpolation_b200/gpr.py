@@ -99,7 +99,8 @@ class Handle:
         return nlz, grad
 
     def make_params(self, radius_m, t_pred, prior_mean, x0=None, mode=0, grad_convention=0, maxiter=0,
-                    gtol=0.0, scratch_gib=0.0, max_active=0, n_groups=0):
+                    gtol=0.0, scratch_gib=0.0, max_active=0, n_groups=0, engine=0, group_size=0,
+                    evals_per_launch=0):
         p = _lib.OiParams()
         p.radius_m, p.t_pred, p.prior_mean = float(radius_m), float(t_pred), float(prior_mean)
         x0 = [0.0] * 5 if x0 is None else list(x0)
@@ -108,7 +109,7 @@ class Handle:
             p.x0[i] = float(v)
         p.mode, p.grad_convention, p.maxiter = int(mode), int(grad_convention), int(maxiter)
         p.gtol, p.scratch_gib, p.max_active = float(gtol), float(scratch_gib), int(max_active)
-        p.n_groups = int(n_groups)
+        p.n_groups, p.engine, p.group_size, p.evals_per_launch = int(n_groups), int(engine), int(group_size), int(evals_per_launch)
         return p
 
     def run(self, params, hypers_in=None):
@@ -128,7 +129,7 @@ class Handle:
     def stats(self) -> dict:
         s = _lib.OiStats()
         self._check(self._L.oi_get_stats(self._h, C.byref(s)))
-        return {k: getattr(s, k) for k, _ in s._fields_}
+        return {k: (list(getattr(s, k)) if k == "cycles_phase" else getattr(s, k)) for k, _ in s._fields_}
 
     def gpr_day(self, x, y, t, z, X, params, hypers_in=None):
         """The whole day through the single ABI call (host buffers in, host buffers out)."""

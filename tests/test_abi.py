@@ -30,8 +30,22 @@ def test_header_symbols_exported(lib):
 def test_struct_layout_matches_header():
     import ctypes as C
     from optimalinterpolation_b200 import _lib
-    assert C.sizeof(_lib.OiParams) == 3 * 8 + 4 * 4 + 6 * 8 + 2 * 8 + 2 * 4
-    assert C.sizeof(_lib.OiStats) == 9 * 8 + 7 * 8 + 3 * 8 + 3 * 8
+    L = C.CDLL(_lib.LIB_PATH)
+    # the library reports sizeof() of its own structs; field order is checked against the header text
+    assert C.sizeof(_lib.OiParams) == L.oi_sizeof_params()
+    assert C.sizeof(_lib.OiStats) == L.oi_sizeof_stats()
+    hdr = open(os.path.join(ROOT, "include", "oi_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    for cname, cls in (("oi_params", _lib.OiParams), ("oi_stats", _lib.OiStats)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), hdr, flags=re.S).group(1)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = decl.split(None, 1)[1]
+            fields += [re.sub(r"\[.*?\]", "", n).strip() for n in names.split(",")]
+        assert fields == [f for f, _ in cls._fields_], cname
 
 
 def test_no_cpu_fallback(lib):
@@ -47,6 +61,6 @@ def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "optimalinterpolation_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".h")):
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f

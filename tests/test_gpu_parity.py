@@ -178,3 +178,26 @@ def test_fit_matches_oracle(small_day, small_oracle):
     # small tail of cells may land elsewhere; on this 52-cell sample allow 3 of them
     assert np.mean(dfs <= 1.0) >= 0.94
     assert np.mean(ok_nl) >= 0.90
+
+
+def test_engines_and_groupings_bit_identical(small_day):
+    """The lockstep engine with 1 or 8 stream groups and tiny batches, and the persistent group engine with
+    group sizes 1, 3 and 8, all run the same tile code: fitted outputs, nfev and status must be bit-identical
+    (=> results do not depend on batch composition, scheduling or GPU count)."""
+    import optimalinterpolation_b200 as oi
+    d = small_day
+    cells = np.linspace(0, len(d.X) - 1, 30).round().astype(int)
+    h = oi.Handle(0)
+    h.set_observations(d.x_train, d.y_train, d.t_train, d.z); h.set_cells(d.X[cells]); h.gather_neighbours(d.radius_km * 1000.0)
+    ref = None
+    for kw in (dict(engine=0, n_groups=1), dict(engine=0, n_groups=8), dict(engine=0, n_groups=3, max_active=7),
+               dict(engine=1, group_size=1), dict(engine=1, group_size=3, evals_per_launch=5), dict(engine=1, group_size=8)):
+        h.run(h.make_params(d.radius_km * 1000.0, d.T_mid, d.mean, d.x0, mode=0, **kw))
+        r = h.get_results()
+        if ref is None:
+            ref = r
+            assert np.isfinite(r["out"][:, 0]).mean() > 0.8
+        else:
+            assert np.array_equal(r["out"], ref["out"], equal_nan=True), kw
+            assert np.array_equal(r["nfev"], ref["nfev"]) and np.array_equal(r["status"], ref["status"]), kw
+    h.close()

@@ -16,7 +16,12 @@ print("cells", len(cells), "wall s", dt, "cells/s", len(cells) / dt)
 print(json.dumps(st))
 print("TFLOP/s overall", st["flops"] / st["ms_total"] * 1e-9, "factor kernels", st["flops_factor"] / st["ms_factor"] * 1e-9)
 for k in ("chol", "trtri", "lauum"):
-    print(k, "TFLOP/s", st["flops_" + k] / st["ms_" + k] * 1e-9, "ms", st["ms_" + k])
+    if st["ms_" + k] > 0:
+        print(k, "TFLOP/s", st["flops_" + k] / st["ms_" + k] * 1e-9, "ms", st["ms_" + k])
+if st["launches_persistent"]:
+    cyc = st["cycles_phase"]; tot = sum(cyc) or 1
+    print("persistent launches", st["launches_persistent"], "phase shares (build, chol, scale, fwd+trtri, alpha, lauum, finalize, idle):",
+          [round(c / tot, 3) for c in cyc])
 print("nfev mean", res["nfev"].mean(), "max", res["nfev"].max(), "status hist", np.bincount(res["status"]))
 print("n mean", res["n"].mean(), "out finite frac", np.isfinite(res["out"][:, 0]).mean())
 np.save("gpurun_out/day_stripe_out.npy", res["out"])
