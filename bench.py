@@ -4,7 +4,9 @@
 A step = one pass of the hot path (neighbour gather -> lockstep CG fit -> posterior) over one batch
 of cells: ``2 x --gpus N`` stripes of the day (stripe s = every 16th ice cell starting at s, so each
 stripe has the day's n-histogram; ~1195 cells per stripe, 2 stripes = 1/8 day per GPU and step,
-per-GPU work fixed => weak scaling; at N=8 one step is the whole day).  Cells of a step are sharded over ranks by LPT on n^3
+per-GPU work fixed => weak scaling; at N=8 one step is the whole day sharded over the 8 GPUs =
+BASELINE.json configs[2]).  At N=1 the whole day (configs[1], ~2.5 min) is additionally run ONCE through
+the same ABI call and reported under "full_day"; it is too long to be the repeated step.  Cells of a step are sharded over ranks by LPT on n^3
 (optimalinterpolation_b200/shard.py); the only collective is the final gather of the result rows.
 
   value : cells/s with observations + cell coordinates already resident in HBM (timed: gather +
@@ -39,6 +41,9 @@ def parse():
     ap.add_argument("--stripes-per-gpu", type=int, default=2)
     ap.add_argument("--max-active", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-day", action="store_true", help="skip the single whole-day pass (N=1 only, ~2.5 min)")
+    ap.add_argument("--no-family-pass", action="store_true", help="skip the single-stream pass that times each kernel family")
+    ap.add_argument("--groups", type=int, default=0, help="lockstep stream groups (0 = library default)")
     ap.add_argument("--cpu-frac", type=float, default=0.2, help="cheapest fraction of cells the CPU sample is drawn from")
     return ap.parse_args()
 
@@ -157,7 +162,8 @@ def main():
     parts = lpt_partition(counts_step, world)
     mine = parts[rank]
     Xmine = pinned(Xstep[mine])
-    params = h.make_params(day.radius_km * 1000.0, day.T_mid, day.mean, day.x0, mode=0, max_active=args.max_active)
+    params = h.make_params(day.radius_km * 1000.0, day.T_mid, day.mean, day.x0, mode=0, max_active=args.max_active,
+                           n_groups=args.groups)
 
     def step_resident():
         h.gather_neighbours(day.radius_km * 1000.0)
@@ -185,7 +191,8 @@ def main():
     for _ in range(args.steps):
         res, st, full = step_resident()
         for k, v in st.items():
-            agg[k] = agg.get(k, 0) + v
+            if not isinstance(v, list):
+                agg[k] = agg.get(k, 0) + v
     e1.record(stream); barrier()
     wall = time.perf_counter() - t0
     sampler.stop_flag = True
@@ -212,6 +219,27 @@ def main():
     d2h = len(mine) * (64 + 12)
     same = bool(np.array_equal(full, full_e, equal_nan=True))
 
+    # ---------------- single-stream pass: device time of each kernel family (diagnostic, untimed) ----------------
+    # With several stream groups the families of different groups overlap, so their per-stream times do not
+    # add up; one extra step with n_groups=1 gives the per-family numbers that the ncu launch list is compared to.
+    fam1 = None
+    if rank == 0 and not args.no_family_pass:
+        p1 = h.make_params(day.radius_km * 1000.0, day.T_mid, day.mean, day.x0, mode=0, max_active=args.max_active, n_groups=1)
+        h.set_cells(Xmine); h.gather_neighbours(day.radius_km * 1000.0); h.run(p1)
+        fam1 = h.stats()
+    # ---------------- the whole day in one call on one GPU (BASELINE.json configs[1]) ----------------
+    full_day = None
+    if world == 1 and not args.no_full_day:
+        Xday = pinned(day.X)
+        t0 = time.perf_counter(); e0.record(stream)
+        res_d = h.gpr_day(px, py, pt, pz, Xday, params)
+        e1.record(stream); torch.cuda.synchronize()
+        sec = max(e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0)
+        st_d = h.stats()
+        full_day = {"cells": int(len(day.X)), "seconds": sec, "cells_per_s": len(day.X) / sec,
+                    "tflops": st_d["flops"] / sec * 1e-12, "evals": int(st_d["n_evals"]), "iterations": int(st_d["n_iterations"]),
+                    "finite_frac": float(np.isfinite(res_d["out"][:, 0]).mean()),
+                    "how": "one oi_gpr_day call with host buffers (H2D + gather + fit + predict + D2H), single pass, not part of the timed steps"}
     if rank == 0:
         # measured FP64 peak (MEASURED_PEAKS.json holds no FP64 entry): cuBLAS DGEMM 8192^3
         a = torch.randn(8192, 8192, dtype=torch.float64, device=dev); b = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
@@ -223,24 +251,35 @@ def main():
             p0.record(); a @ b; p1.record(); torch.cuda.synchronize(); best = min(best, p0.elapsed_time(p1))
         peak_tf = 2 * 8192 ** 3 / best * 1e-9
         del a, b
-        fam = {k: (agg["ms_" + k], agg["flops_" + k], agg["launches_" + k]) for k in ("chol", "trtri", "lauum")}
-        top = max(fam, key=lambda k: fam[k][0])
-        names = {"chol": "k_chol_update+k_chol_panel", "trtri": "k_trtri", "lauum": "k_lauum_trace"}
-        ach = fam[top][1] / fam[top][0] * 1e-9
+        # dominant kernel family = the FP64 DMMA tile kernels (one gemm_nt_stream core: k_chol_update, k_chol_panel,
+        # k_scale_rows, k_trtri, k_lauum_trace).  achieved = their algorithmic flops / the device time of the whole
+        # lockstep region of the timed steps (a lower bound: build, substitutions, finalize and host gaps included).
+        ach = agg["flops_factor"] / agg["ms_total"] * 1e-9
+        dmma_launches = agg["launches_chol"] + agg["launches_trtri"] + agg["launches_lauum"]
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("dmma_tile_kernels")
         except Exception:
             pass
-        roofline = {"bound": "tensor", "kernel": names[top], "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": ach / peak_tf, "traffic": traffic,
+        roofline = {"bound": "tensor", "kernel": "FP64 DMMA tile kernels (k_chol_update+k_chol_panel+k_scale_rows+k_trtri+k_lauum_trace)",
+                    "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry; "
                                    "DMMA issue-rate microbenchmark: 37.1 TFLOP/s, profiles/r01_fp64_peak_microbench.txt)",
-                    "flops_per_launch": fam[top][1] / max(fam[top][2], 1), "ms_per_launch": fam[top][0] / max(fam[top][2], 1),
-                    "share_of_step": fam[top][0] / agg["ms_total"],
-                    "families": {names[k]: {"tflops": fam[k][1] / fam[k][0] * 1e-9, "ms": fam[k][0] / args.steps,
-                                            "share": fam[k][0] / agg["ms_total"]} for k in fam},
+                    "flops_per_launch": agg["flops_factor"] / max(dmma_launches, 1),
+                    "ms_per_launch": agg["ms_total"] / max(dmma_launches, 1),
+                    "how": f"{int(st['n_groups'])} stream groups overlap their kernels, so the time base is the device time of the "
+                           "whole lockstep region of the timed steps (CUDA events on the launching stream), not a sum of launches",
                     "whole_step_tflops": agg["flops"] / (ms * 1e-3) * 1e-12 if world == 1 else None}
+        if fam1 is not None:
+            names = {"chol": "k_chol_update+k_chol_panel+k_scale_rows", "trtri": "k_trtri", "lauum": "k_lauum_trace"}
+            roofline["families_single_stream"] = {
+                names[k]: {"tflops": fam1["flops_" + k] / fam1["ms_" + k] * 1e-9, "ms": fam1["ms_" + k],
+                           "share": fam1["ms_" + k] / fam1["ms_total"], "launches": int(fam1["launches_" + k])}
+                for k in names}
+            roofline["families_single_stream"]["other (k_build, k_fwd, k_alpha, k_finalize)"] = {
+                "ms": fam1["ms_build"] + fam1["ms_fwd"] + fam1["ms_alpha"] + fam1["ms_finalize"],
+                "share": (fam1["ms_build"] + fam1["ms_fwd"] + fam1["ms_alpha"] + fam1["ms_finalize"]) / fam1["ms_total"]}
+            roofline["share_of_step"] = sum(fam1["ms_" + k] for k in names) / fam1["ms_total"]
         line = {
             "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -261,6 +300,8 @@ def main():
             "iterations_per_step": agg["n_iterations"] / args.steps,
             "roofline": roofline,
         }
+        if full_day is not None:
+            line["full_day"] = full_day
         if world == 1 and not args.no_cpu_baseline:
             import warnings
             warnings.simplefilter("ignore")

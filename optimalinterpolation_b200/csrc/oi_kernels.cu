@@ -7,6 +7,9 @@
 //   k_build ... k_finalize              lockstep engine: one launch per algorithmic step over all active cells
 //
 // Compiled with -fmad=false (see oi_optim.cuh); hot scalar loops use explicit fma().
+#ifndef OI_PIPE_MINB
+#define OI_PIPE_MINB 4      // resident CTAs per SM the pipeline-only kernels are compiled for (48 KB of shared memory each)
+#endif
 #include "oi_tiles.cuh"
 #include "oi_optim.cuh"
 
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(OI_THREADS) k_build(const OiSlot* __restrict__
     tile_build(s, ca, pk, i, j, smem);
 }
 
-__global__ void __launch_bounds__(OI_THREADS) k_chol_update(const OiSlot* __restrict__ slots, int k) {
+__global__ void __launch_bounds__(OI_THREADS, 3) k_chol_update(const OiSlot* __restrict__ slots, int k) {
     extern __shared__ __align__(16) double smem[];
     const OiSlot s = slots[blockIdx.y];
     const int i = k + blockIdx.x;
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(OI_THREADS) k_chol_update(const OiSlot* __rest
     tile_chol_update(s, i, k, smem);
 }
 
-__global__ void __launch_bounds__(OI_THREADS) k_chol_panel(const OiSlot* __restrict__ slots, int k) {
+__global__ void __launch_bounds__(OI_THREADS, OI_PIPE_MINB) k_chol_panel(const OiSlot* __restrict__ slots, int k) {
     extern __shared__ __align__(16) double smem[];
     const OiSlot s = slots[blockIdx.y];
     const int i = k + 1 + blockIdx.x;
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(256) k_fwd(const OiSlot* __restrict__ slots, O
     cell_fwd(s, ca, pk, t_pred, ca.phase[s.cell] == OI_PH_PREDICT, smem);
 }
 
-__global__ void __launch_bounds__(OI_THREADS) k_scale_rows(const OiSlot* __restrict__ slots, int row) {
+__global__ void __launch_bounds__(OI_THREADS, 3) k_scale_rows(const OiSlot* __restrict__ slots, int row) {
     extern __shared__ __align__(16) double smem[];
     const OiSlot s = slots[blockIdx.y];
     int i, j;
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(OI_THREADS) k_scale_rows(const OiSlot* __restr
     tile_scale(s, i, j, smem);
 }
 
-__global__ void __launch_bounds__(OI_THREADS) k_trtri(const OiSlot* __restrict__ slots, const int* __restrict__ phase, int d) {
+__global__ void __launch_bounds__(OI_THREADS, OI_PIPE_MINB) k_trtri(const OiSlot* __restrict__ slots, const int* __restrict__ phase, int d) {
     extern __shared__ __align__(16) double smem[];
     const OiSlot s = slots[blockIdx.y];
     const int kb = blockIdx.x;
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(OI_THREADS) k_alpha(const OiSlot* __restrict__
     rows_alpha(s, rb);
 }
 
-__global__ void __launch_bounds__(OI_THREADS) k_lauum_trace(const OiSlot* __restrict__ slots, OiCellArrays ca, OiPacked pk, int row) {
+__global__ void __launch_bounds__(OI_THREADS, OI_PIPE_MINB) k_lauum_trace(const OiSlot* __restrict__ slots, OiCellArrays ca, OiPacked pk, int row) {
     extern __shared__ __align__(16) double smem[];
     const OiSlot s = slots[blockIdx.y];
     int i, j;

@@ -8,7 +8,10 @@
 #define OI_DEFAULT_GROUPS 8
 #define OI_DEFAULT_GROUP_SIZE 4        // CTAs per group of the persistent engine while cells are plentiful
 #define OI_SMEM_BYTES (2 * OI_NB * 68 * 8 + 4 * 64 * 8 + 16)   // T + W of the diagonal factor + per-warp scratch + flag (>= the cp.async pipeline)
-#define OI_SMEM_PIPE (3 * 2 * OI_NB * 20 * 8)                  // 3-stage cp.async pipeline of two 64x16 operand chunks
+#ifndef STAGES
+#define STAGES 3
+#endif
+#define OI_SMEM_PIPE (STAGES * 2 * OI_NB * 16 * 8)              // cp.async pipeline stages of two swizzled 64x16 operand chunks
 
 struct OiRunConst {
     double mean, gtol;

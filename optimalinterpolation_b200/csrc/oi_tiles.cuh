@@ -32,11 +32,12 @@
 
 #define NB OI_NB
 #define KT 16
-#define LDS_ (KT + 4)          // smem row stride (doubles) of a streamed operand chunk: conflict-free DMMA fragment loads
+#ifndef STAGES
 #define STAGES 3
+#endif
 #define GEMM_THREADS OI_THREADS
 #define TS 68                  // smem row stride of a resident 64x64 tile
-#define STAGE_DOUBLES (2 * NB * LDS_)
+#define STAGE_DOUBLES (2 * NB * KT)   // operand chunks are stored unpadded (64 rows x 128 B) with an XOR swizzle
 #define PIPE_BYTES (STAGES * STAGE_DOUBLES * 8)
 
 #define ROOT3 1.7320508075688772   // np.sqrt(3.)
@@ -119,18 +120,23 @@ __device__ __forceinline__ void tile_build(const OiSlot& s, const OiCellArrays& 
 
 // ------------------------------------------------------------------------------------------
 // FP64 DMMA tile core: acc(64x64) += A(64 x [k0,k1)) * B(64 x [k0,k1))^T, both K-contiguous.
-// 4 warps (2x2), warp tile 32x32 = 4x4 m8n8k4 tiles, 3-stage cp.async pipeline of 16-wide chunks.
+// 4 warps (2x2), warp tile 32x32 = 4x4 m8n8k4 tiles, STAGES-deep cp.async pipeline of 16-wide chunks.
 // ------------------------------------------------------------------------------------------
+// Shared-memory layout of a streamed 64x16 operand chunk: row r occupies 128 B; its eight 16-byte pieces are
+// stored at piece index (p ^ (r & 7)).  cp.async writes stay 16-byte aligned and the DMMA fragment loads
+// (8 rows x 4 consecutive doubles per instruction) touch every bank pair exactly twice = the two wavefronts
+// a 64-bit warp load needs anyway: conflict-free without padding, so a stage is 16 KB instead of 20 KB.
 __device__ __forceinline__ void load_stage(double* st, const double* __restrict__ A, long long lda,
                                            const double* __restrict__ B, long long ldb, int kk, int tid) {
     double* As = st;
-    double* Bs = st + NB * LDS_;
+    double* Bs = st + NB * KT;
 #pragma unroll
     for (int it = 0; it < 4; it++) {
         int c = tid + it * GEMM_THREADS;      // 0..511
-        int row = c >> 3, col = (c & 7) * 2;
-        cp_async16(&As[row * LDS_ + col], &A[(long long)row * lda + kk + col]);
-        cp_async16(&Bs[row * LDS_ + col], &B[(long long)row * ldb + kk + col]);
+        int row = c >> 3, p = c & 7;
+        int dst = row * KT + ((p ^ (row & 7)) << 1);
+        cp_async16(&As[dst], &A[(long long)row * lda + kk + p * 2]);
+        cp_async16(&Bs[dst], &B[(long long)row * ldb + kk + p * 2]);
     }
 }
 
@@ -145,17 +151,24 @@ __device__ __forceinline__ int clamp024(int v) { return v <= 0 ? 0 : (v >= 32 ? 
 __device__ __forceinline__ int hi_lt(int w, int limit) { return clamp024(limit - w * 32); }
 __device__ __forceinline__ int lo_ge(int w, int limit) { return clamp024(limit - w * 32); }
 
+// (mma.sync m16n8k16.f64 was tried: ptxas lowers it to eight DMMA.8x8x4 on sm_100a -- the hardware shape --
+// so it brings no instruction-count saving; the m8n8k4 form is kept.)
 template <int MLO, int MHI, int NLO, int NHI>
-__device__ __forceinline__ void mma_chunk_t(double (&acc)[4][4][2], const double* As, const double* Bs, int lda_s, int ldb_s,
-                                            int wm, int wn, int lane, int kofs, int ksteps) {
+__device__ __forceinline__ void mma_chunk_t(double (&acc)[4][4][2], const double* As, const double* Bs, int wm, int wn, int lane) {
     const int fr = lane >> 2, fc = lane & 3;
+    const double* Ar = As + (wm * 32 + fr) * KT;
+    const double* Br = Bs + (wn * 32 + fr) * KT;
+    // column ks*4+fc of a row with (row & 7) == fr sits at swizzled offset sw[ks]
+    int sw[KT / 4];
 #pragma unroll
-    for (int ks = 0; ks < ksteps; ks++) {
+    for (int ks = 0; ks < KT / 4; ks++) sw[ks] = (((ks * 2 + (fc >> 1)) ^ fr) << 1) + (fc & 1);
+#pragma unroll
+    for (int ks = 0; ks < KT / 4; ks++) {
         double a[4], b[4];
 #pragma unroll
-        for (int mb = MLO; mb < MHI; mb++) a[mb] = As[(wm * 32 + mb * 8 + fr) * lda_s + kofs + ks * 4 + fc];
+        for (int mb = MLO; mb < MHI; mb++) a[mb] = Ar[mb * 8 * KT + sw[ks]];
 #pragma unroll
-        for (int nb = NLO; nb < NHI; nb++) b[nb] = Bs[(wn * 32 + nb * 8 + fr) * ldb_s + kofs + ks * 4 + fc];
+        for (int nb = NLO; nb < NHI; nb++) b[nb] = Br[nb * 8 * KT + sw[ks]];
 #pragma unroll
         for (int mb = MLO; mb < MHI; mb++)
 #pragma unroll
@@ -163,17 +176,16 @@ __device__ __forceinline__ void mma_chunk_t(double (&acc)[4][4][2], const double
     }
 }
 template <int MLO, int MHI>
-__device__ __forceinline__ void mma_chunk_n(double (&acc)[4][4][2], const double* As, const double* Bs, int lda_s, int ldb_s,
-                                            int wm, int wn, int lane, int kofs, int ksteps, int nlo, int nhi) {
-    if (nlo == 0 && nhi == 4) mma_chunk_t<MLO, MHI, 0, 4>(acc, As, Bs, lda_s, ldb_s, wm, wn, lane, kofs, ksteps);
-    else if (nlo == 0 && nhi == 2) mma_chunk_t<MLO, MHI, 0, 2>(acc, As, Bs, lda_s, ldb_s, wm, wn, lane, kofs, ksteps);
-    else if (nlo == 2 && nhi == 4) mma_chunk_t<MLO, MHI, 2, 4>(acc, As, Bs, lda_s, ldb_s, wm, wn, lane, kofs, ksteps);
+__device__ __forceinline__ void mma_chunk_n(double (&acc)[4][4][2], const double* As, const double* Bs, int wm, int wn, int lane,
+                                            int nlo, int nhi) {
+    if (nlo == 0 && nhi == 4) mma_chunk_t<MLO, MHI, 0, 4>(acc, As, Bs, wm, wn, lane);
+    else if (nlo == 0 && nhi == 2) mma_chunk_t<MLO, MHI, 0, 2>(acc, As, Bs, wm, wn, lane);
+    else if (nlo == 2 && nhi == 4) mma_chunk_t<MLO, MHI, 2, 4>(acc, As, Bs, wm, wn, lane);
 }
-__device__ __forceinline__ void mma_chunk(double (&acc)[4][4][2], const double* As, const double* Bs, int lda_s, int ldb_s,
-                                          int wm, int wn, int lane, int kofs, int ksteps, SubRange r) {
-    if (r.mlo == 0 && r.mhi == 4) mma_chunk_n<0, 4>(acc, As, Bs, lda_s, ldb_s, wm, wn, lane, kofs, ksteps, r.nlo, r.nhi);
-    else if (r.mlo == 0 && r.mhi == 2) mma_chunk_n<0, 2>(acc, As, Bs, lda_s, ldb_s, wm, wn, lane, kofs, ksteps, r.nlo, r.nhi);
-    else if (r.mlo == 2 && r.mhi == 4) mma_chunk_n<2, 4>(acc, As, Bs, lda_s, ldb_s, wm, wn, lane, kofs, ksteps, r.nlo, r.nhi);
+__device__ __forceinline__ void mma_chunk(double (&acc)[4][4][2], const double* As, const double* Bs, int wm, int wn, int lane, SubRange r) {
+    if (r.mlo == 0 && r.mhi == 4) mma_chunk_n<0, 4>(acc, As, Bs, wm, wn, lane, r.nlo, r.nhi);
+    else if (r.mlo == 0 && r.mhi == 2) mma_chunk_n<0, 2>(acc, As, Bs, wm, wn, lane, r.nlo, r.nhi);
+    else if (r.mlo == 2 && r.mhi == 4) mma_chunk_n<2, 4>(acc, As, Bs, wm, wn, lane, r.nlo, r.nhi);
 }
 
 // The pipeline starts with a CTA barrier (the shared-memory buffers may still be in use by the previous tile
@@ -198,7 +210,7 @@ __device__ __forceinline__ void gemm_nt_stream(double (&acc)[4][4][2], const dou
         if (nx < nk) load_stage(smem + (nx % STAGES) * STAGE_DOUBLES, A, lda, B, ldb, k0 + nx * KT, tid);
         cp_async_commit();
         const double* st = smem + (it % STAGES) * STAGE_DOUBLES;
-        mma_chunk(acc, st, st + NB * LDS_, LDS_, LDS_, wm, wn, lane, 0, KT / 4, maskfn(k0 + it * KT));
+        mma_chunk(acc, st, st + NB * KT, wm, wn, lane, maskfn(k0 + it * KT));
     }
     cp_async_wait<0>();
     __syncthreads();

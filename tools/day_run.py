@@ -2,6 +2,9 @@
 import sys, os, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
+from optimalinterpolation_b200 import _lib
+if os.environ.get("OI_LIB"):
+    _lib.LIB_PATH = os.environ["OI_LIB"]
 import optimalinterpolation_b200 as oi
 from optimalinterpolation_b200.synthetic import make_day
 
@@ -13,7 +16,6 @@ g = oi.GPRDay(d.x_train, d.y_train, d.t_train, d.z, d.X[cells], d.radius_km, d.m
 t0 = time.time(); res = g.run(opt=True, max_active=max_active); dt = time.time() - t0
 st = g.handle.stats()
 print("cells", len(cells), "wall s", dt, "cells/s", len(cells) / dt)
-print(json.dumps(st))
 print("TFLOP/s overall", st["flops"] / st["ms_total"] * 1e-9, "factor kernels", st["flops_factor"] / st["ms_factor"] * 1e-9)
 for k in ("chol", "trtri", "lauum"):
     if st["ms_" + k] > 0:
