@@ -86,6 +86,9 @@ typedef struct oi_stats {
     int64_t n_groups;       /* groups used (last launch); lockstep engine with > 1: the per-family ms_* are per-stream times that overlap */
     int64_t group_size;     /* persistent engine: CTAs per group of the last launch                      */
     int64_t launches_persistent;
+    int64_t n_graph_captures, n_graph_launches; /* lockstep engine: small-batch iterations replayed as CUDA graphs */
+    double ms_graph;        /* device time of those iterations (not split by kernel family)              */
+    int64_t n_express_cells; /* lockstep engine: cells handed to the express lanes (long optimiser runs)           */
     double ms_persistent;   /* device time inside k_gp_persistent (CUDA events)                          */
     double cycles_phase[8]; /* persistent engine: CTA clock cycles per phase summed over CTAs:
                                build, chol, scale, fwd+trtri, alpha, lauum+trace, finalize, idle/queue   */

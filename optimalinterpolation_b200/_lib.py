@@ -30,7 +30,8 @@ class OiStats(C.Structure):
                 ("ms_alpha", C.c_double), ("ms_lauum", C.c_double), ("ms_finalize", C.c_double),
                 ("flops_chol", C.c_double), ("flops_trtri", C.c_double), ("flops_lauum", C.c_double),
                 ("launches_chol", C.c_int64), ("launches_trtri", C.c_int64), ("launches_lauum", C.c_int64),
-                ("n_groups", C.c_int64), ("group_size", C.c_int64), ("launches_persistent", C.c_int64),
+                ("n_groups", C.c_int64), ("group_size", C.c_int64), ("launches_persistent", C.c_int64), ("n_graph_captures", C.c_int64), ("n_graph_launches", C.c_int64), ("ms_graph", C.c_double),
+                ("n_express_cells", C.c_int64),
                 ("ms_persistent", C.c_double), ("cycles_phase", C.c_double * 8)]
 
 

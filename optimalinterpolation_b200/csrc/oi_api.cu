@@ -4,6 +4,8 @@
 // posterior) for ALL active cells at once, each cell at the point its own optimiser asked for.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <deque>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -237,6 +239,10 @@ struct OiGroup {
     OiSlot *d_slots = nullptr, *h_slots = nullptr;
     int *d_slot_phase = nullptr, *h_slot_phase = nullptr, *d_fail = nullptr;
     char* arena = nullptr; size_t arena_bytes = 0, used = 0;
+    long long tiles = 0;            // sum of N(N+1)/2 over the active cells (work admitted to the group)
+    bool high_prio = false;
+    // CUDA graph of one iteration, replayed while the (small) batch keeps its composition
+    cudaGraphExec_t gexec = nullptr; std::vector<int> gcells, last_cells; int same_count = 0; bool graph_mode = false;
     int slot_cap = 0;
     std::vector<int> active, cnt_gt;
     bool in_flight = false;
@@ -274,6 +280,7 @@ static void free_groups(oi_handle* h) {
     for (OiGroup* g : h->groups) {
         for (auto& e : g->ev) if (e) cudaEventDestroy(e);
         if (g->done) cudaEventDestroy(g->done);
+        if (g->gexec) cudaGraphExecDestroy(g->gexec);
         if (g->st) cudaStreamDestroy(g->st);
         delete g;
     }
@@ -285,13 +292,66 @@ struct LockstepRun {
     std::vector<int> pending; size_t next = 0;
     OiPacked pk; FILE* trace = nullptr;
     double ms_factor = 0;
+    // express lanes: the last n_express groups only take cells that already spent express_after iterations in a
+    // bulk group.  Such cells (line searches that keep failing, maxiter) need up to ~2000 evaluations; in a small
+    // batch an iteration takes ~1 ms instead of the ~10 ms of a full bulk batch, so their long dependent chains
+    // finish underneath the bulk work instead of forming a serial tail after it.
+    int G = 1, n_express = 0, express_after = 0, express_cap = 0;
+    std::deque<int> express_pending;
+    std::vector<int> iters;
+
+    long long tile_budget = 0;      // per bulk group
+    bool is_express(int gi) const { return gi >= G - n_express; }
+    long long cell_tiles(int c) const { long long N = (h->h_counts[c] + OI_NB - 1) / OI_NB; return N * (N + 1) / 2; }
+
+    int graph_max_A = 0;            // batches up to this many cells replay a captured graph
+
+    // the kernel chain of one lockstep iteration of group g (timed: with the family boundary events)
+    int launch_chain(OiGroup& g, int A, int Nmax, const int* cg, cudaStream_t st, bool timed) {
+        if (timed) CK(cudaEventRecord(g.ev[0], st));
+        oi_launch_build(g.d_slots, A, Nmax, cg, h->ca, pk, st);
+        if (timed) CK(cudaEventRecord(g.ev[1], st));
+        for (int k = 0; k < Nmax; k++) {
+            oi_launch_chol_update(g.d_slots, A, Nmax, cg, k, st);
+            oi_launch_chol_panel(g.d_slots, A, Nmax, cg, k, st);
+        }
+        oi_launch_scale_rows(g.d_slots, A, Nmax, cg, st);
+        if (timed) CK(cudaEventRecord(g.ev[2], st));
+        oi_launch_fwd(g.d_slots, A, h->ca, pk, t_pred, st);
+        if (timed) CK(cudaEventRecord(g.ev[3], st));
+        for (int d = 1; d < Nmax; d++) oi_launch_trtri(g.d_slots, A, Nmax, cg, d, h->ca.phase, st);
+        if (timed) CK(cudaEventRecord(g.ev[4], st));
+        oi_launch_alpha(g.d_slots, A, Nmax, h->ca.phase, st);
+        if (timed) CK(cudaEventRecord(g.ev[5], st));
+        oi_launch_lauum_trace(g.d_slots, A, Nmax, cg, h->ca, pk, st);
+        if (timed) CK(cudaEventRecord(g.ev[6], st));
+        oi_launch_finalize(g.d_slots, A, h->ca, rc, g.d_slot_phase, st);
+        if (timed) CK(cudaEventRecord(g.ev[7], st));
+        return OI_OK;
+    }
 
     // admit pending cells (largest first) into group g, pack its slot table and queue one iteration
     int issue(OiGroup& g, int gi) {
-        while (next < pending.size() && (int)g.active.size() < g.slot_cap) {
-            size_t need = slot_bytes(h->h_counts[pending[next]]);
-            if (g.used + need > g.arena_bytes) break;
-            g.used += need; g.active.push_back(pending[next++]);
+        const int cap = is_express(gi) ? std::min(express_cap, g.slot_cap) : g.slot_cap;
+        if (!is_express(gi)) {
+            while (next < pending.size() && (int)g.active.size() < cap) {
+                const int c = pending[next];
+                size_t need = slot_bytes(h->h_counts[c]);
+                if (g.used + need > g.arena_bytes) break;
+                if (!g.active.empty() && g.tiles + cell_tiles(c) > tile_budget) break;   // enough work to fill the GPU share
+                g.used += need; g.tiles += cell_tiles(c); g.active.push_back(c); next++;
+            }
+        }
+        // express cells go to the express lanes; once the bulk list is exhausted, bulk groups whose own batch has
+        // become small help out
+        if (is_express(gi) || (next >= pending.size() && (int)g.active.size() < express_cap)) {
+            const int xcap = std::min(cap, express_cap);
+            while (!express_pending.empty() && (int)g.active.size() < xcap) {
+                size_t need = slot_bytes(h->h_counts[express_pending.front()]);
+                if (g.used + need > g.arena_bytes) break;
+                g.used += need; g.tiles += cell_tiles(express_pending.front());
+                g.active.push_back(express_pending.front()); express_pending.pop_front();
+            }
         }
         g.in_flight = false;
         if (g.active.empty()) return OI_OK;
@@ -326,25 +386,38 @@ struct LockstepRun {
         const int* cg = g.cnt_gt.data();
         cudaStream_t st = g.st;
         CK(cudaMemcpyAsync(g.d_slots, g.h_slots, (size_t)A * sizeof(OiSlot), cudaMemcpyHostToDevice, st));
-        CK(cudaEventRecord(g.ev[0], st));
-        oi_launch_build(g.d_slots, A, Nmax, cg, h->ca, pk, st);
-        CK(cudaEventRecord(g.ev[1], st));
-        for (int k = 0; k < Nmax; k++) {
-            oi_launch_chol_update(g.d_slots, A, Nmax, cg, k, st);
-            oi_launch_chol_panel(g.d_slots, A, Nmax, cg, k, st);
+        // Small batches (the optimiser's tail) are bound by the host's launch rate and the gaps between ~4N
+        // dependent launches: once a batch has kept its composition for a few iterations, the chain is captured
+        // into a CUDA graph and replayed with one call until a cell leaves.
+        bool use_graph = false;
+        if (graph_max_A > 0 && A <= graph_max_A) {
+            if (g.gexec && g.gcells == g.active) use_graph = true;
+            else {
+                if (g.last_cells == g.active) g.same_count++;
+                else { g.same_count = 0; g.last_cells = g.active; }
+                if (g.same_count >= 2) {
+                    cudaGraph_t graph = nullptr;
+                    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                    launch_chain(g, A, Nmax, cg, st, false);
+                    CK(cudaStreamEndCapture(st, &graph));
+                    if (g.gexec) { cudaGraphExecDestroy(g.gexec); g.gexec = nullptr; }
+                    CK(cudaGraphInstantiate(&g.gexec, graph, 0));
+                    cudaGraphDestroy(graph);
+                    g.gcells = g.active;
+                    use_graph = true;
+                    h->stats.n_graph_captures++;
+                }
+            }
         }
-        oi_launch_scale_rows(g.d_slots, A, Nmax, cg, st);
-        CK(cudaEventRecord(g.ev[2], st));
-        oi_launch_fwd(g.d_slots, A, h->ca, pk, t_pred, st);
-        CK(cudaEventRecord(g.ev[3], st));
-        for (int d = 1; d < Nmax; d++) oi_launch_trtri(g.d_slots, A, Nmax, cg, d, h->ca.phase, st);
-        CK(cudaEventRecord(g.ev[4], st));
-        oi_launch_alpha(g.d_slots, A, Nmax, h->ca.phase, st);
-        CK(cudaEventRecord(g.ev[5], st));
-        oi_launch_lauum_trace(g.d_slots, A, Nmax, cg, h->ca, pk, st);
-        CK(cudaEventRecord(g.ev[6], st));
-        oi_launch_finalize(g.d_slots, A, h->ca, rc, g.d_slot_phase, st);
-        CK(cudaEventRecord(g.ev[7], st));
+        g.graph_mode = use_graph;
+        if (use_graph) {
+            CK(cudaEventRecord(g.ev[0], st));
+            CK(cudaGraphLaunch(g.gexec, st));
+            CK(cudaEventRecord(g.ev[7], st));
+        } else {
+            int r = launch_chain(g, A, Nmax, cg, st, true);
+            if (r) return r;
+        }
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(g.h_slot_phase, g.d_slot_phase, (size_t)A * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(g.done, st));
@@ -356,15 +429,22 @@ struct LockstepRun {
     // wait for group g's iteration, account for it, retire the finished cells
     int retire(OiGroup& g, int gi) {
         CK(cudaEventSynchronize(g.done));
-        float m[7];
-        for (int q = 0; q < 7; q++) cudaEventElapsedTime(&m[q], g.ev[q], g.ev[q + 1]);
+        float m[7] = {0, 0, 0, 0, 0, 0, 0};
         oi_stats& S = h->stats;
+        if (g.graph_mode) {
+            float t = 0; cudaEventElapsedTime(&t, g.ev[0], g.ev[7]);
+            S.ms_graph += t; ms_factor += t; S.n_graph_launches++;
+        } else
+            for (int q = 0; q < 7; q++) cudaEventElapsedTime(&m[q], g.ev[q], g.ev[q + 1]);
         S.ms_build += m[0]; S.ms_chol += m[1]; S.ms_fwd += m[2]; S.ms_trtri += m[3];
         S.ms_alpha += m[4]; S.ms_lauum += m[5]; S.ms_finalize += m[6];
         ms_factor += m[1] + m[3] + m[5];
         const int A = g.A, Nmax = g.Nmax;
-        if (trace) std::fprintf(trace, "%lld,%d,%d,%d,%.4f,%.4f,%.4f,%.4f,%.4f,%.4f,%.4f,%.6g\n", (long long)S.n_iterations, gi, A, Nmax,
-                                m[0], m[1], m[2], m[3], m[4], m[5], m[6], g.flf);
+        if (trace) {
+            float since = 0; cudaEventElapsedTime(&since, h->ev[0], g.ev[7]);     // device time since the fork
+            std::fprintf(trace, "%lld,%d,%d,%d,%.4f,%.4f,%.4f,%.4f,%.4f,%.4f,%.4f,%.6g,%.3f\n", (long long)S.n_iterations, gi, A, Nmax,
+                         m[0], m[1], m[2], m[3], m[4], m[5], m[6], g.flf, since);
+        }
         S.flops += g.fl; S.flops_factor += g.flf; S.n_evals += g.nev;
         S.flops_chol += g.flf_chol; S.flops_trtri += g.flf_fit / 3; S.flops_lauum += g.flf_fit / 3;
         const bool roww = A >= OI_ROWWISE_MIN_SLOTS_HOST;
@@ -374,11 +454,16 @@ struct LockstepRun {
         S.n_launches += (roww ? Nmax : 1) + (2 * Nmax - 1) + (Nmax > 1 ? (roww ? Nmax - 1 : 1) : 0) + 1 + std::max(0, Nmax - 1) + 1 +
                         (roww ? Nmax : 1) + 1;
         size_t w = 0;
+        const bool bulk = !is_express(gi) && n_express > 0 && A > express_cap;    // only big (slow) batches hand over
         for (int a = 0; a < A; a++) {
             int c = g.active[a];
             h_phase[c] = g.h_slot_phase[a];
-            if (h_phase[c] == OI_PH_DONE) g.used -= slot_bytes(h->h_counts[c]);
-            else g.active[w++] = c;
+            if (h_phase[c] == OI_PH_DONE) { g.used -= slot_bytes(h->h_counts[c]); g.tiles -= cell_tiles(c); }
+            else if (bulk && ++iters[c] >= express_after && h_phase[c] == OI_PH_FIT) {
+                g.used -= slot_bytes(h->h_counts[c]); g.tiles -= cell_tiles(c);   // hand the long-runner over to an express lane
+                express_pending.push_back(c);
+                S.n_express_cells++;
+            } else g.active[w++] = c;
         }
         g.active.resize(w);
         g.in_flight = false;
@@ -400,7 +485,7 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
     // largest cells first: cost-sorted ragged batches (cost ~ n^3)
     std::stable_sort(pending.begin(), pending.end(), [&](int a, int b) { return h->h_counts[a] > h->h_counts[b]; });
     if (pending.empty()) return OI_OK;
-    if (max_active <= 0) max_active = 2048;
+    if (max_active <= 0) max_active = 8192;
     max_active = std::min<int>(max_active, 65535);
     if (const char* e = std::getenv("OI_GROUPS")) n_groups = std::atoi(e);
     if (n_groups <= 0) n_groups = OI_DEFAULT_GROUPS;
@@ -435,25 +520,78 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
     // OI_TRACE=<file>: one CSV line per group iteration (active cells, Nmax, stream-ms per kernel family)
     if (const char* tp = std::getenv("OI_TRACE")) {
         R.trace = std::fopen(tp, "a");
-        if (R.trace) std::fprintf(R.trace, "iter,group,active,Nmax,ms_build,ms_chol,ms_fwd,ms_trtri,ms_alpha,ms_lauum,ms_finalize,flops_factor\n");
+        if (R.trace) std::fprintf(R.trace, "iter,group,active,Nmax,ms_build,ms_chol,ms_fwd,ms_trtri,ms_alpha,ms_lauum,ms_finalize,flops_factor,t_ms\n");
+    }
+    R.G = G;
+    R.n_express = G >= 4 ? std::max(1, G / 4) : 0;
+    R.express_after = 224; R.express_cap = 24;
+    if (const char* e = std::getenv("OI_EXPRESS")) R.n_express = std::min(std::max(std::atoi(e), 0), G - 1);
+    if (const char* e = std::getenv("OI_EXPRESS_AFTER")) R.express_after = std::max(std::atoi(e), 1);
+    if (const char* e = std::getenv("OI_EXPRESS_CAP")) R.express_cap = std::max(std::atoi(e), 1);
+    R.iters.assign((size_t)nc, 0);
+    R.graph_max_A = 32;
+    if (const char* e = std::getenv("OI_GRAPH_MAX")) R.graph_max_A = std::max(std::atoi(e), 0);
+    for (int gi = 0; gi < G; gi++) { OiGroup& g = *h->groups[gi]; g.gcells.clear(); g.last_cells.clear(); g.same_count = 0; }
+    // work admitted per bulk group: enough tiles in flight to fill the GPU, few enough that an iteration stays short
+    // (a cell's iteration latency = active work / throughput; long optimiser runs are only recognised by their
+    // iteration count, so latency decides how early they reach an express lane)
+    long long tile_total = 110000;
+    if (const char* e = std::getenv("OI_TILE_BUDGET")) tile_total = std::max(1LL, std::atoll(e));
+    R.tile_budget = std::max(1LL, tile_total / std::max(1, G - R.n_express));
+    {
+        int least = 0, greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        for (int gi = 0; gi < G; gi++) {
+            OiGroup& g = *h->groups[gi];
+            const bool want = R.is_express(gi) && greatest != least;
+            if (g.high_prio != want) {               // express lanes run on high-priority streams
+                CK(cudaStreamSynchronize(g.st));
+                CK(cudaStreamDestroy(g.st));
+                CK(cudaStreamCreateWithPriority(&g.st, cudaStreamNonBlocking, want ? greatest : least));
+                g.high_prio = want;
+            }
+            g.tiles = 0;
+        }
     }
     // fork: the group streams start after everything queued on the handle's stream
     CK(cudaEventRecord(h->ev[0], h->st));
     for (int gi = 0; gi < G; gi++) CK(cudaStreamWaitEvent(h->groups[gi]->st, h->ev[0], 0));
     int rc2 = OI_OK;
     for (int gi = 0; gi < G && !rc2; gi++) rc2 = R.issue(*h->groups[gi], gi);
-    bool any = true;
-    while (!rc2 && any) {
-        any = false;
-        for (int gi = 0; gi < G && !rc2; gi++) {
-            OiGroup& g = *h->groups[gi];
-            if (!g.in_flight) continue;
-            any = true;
-            if ((rc2 = R.retire(g, gi))) break;
-            rc2 = R.issue(g, gi);
+    // event loop: poll the groups (non-blocking), express lanes first and again after every serviced bulk group,
+    // so that their short iterations are never held up behind the host work of a bulk group
+    auto service = [&](int gi, bool& progressed) -> int {
+        OiGroup& g = *h->groups[gi];
+        if (g.in_flight) {
+            cudaError_t q = cudaEventQuery(g.done);
+            if (q == cudaErrorNotReady) return OI_OK;
+            if (q != cudaSuccess) return fail(OI_ERR_CUDA, std::string("run_lockstep: ") + cudaGetErrorString(q));
+            int r = R.retire(g, gi);
+            if (r) return r;
+            progressed = true;
         }
+        int r = R.issue(g, gi);
+        if (g.in_flight) progressed = true;
+        return r;
+    };
+    while (!rc2) {
+        bool progressed = false;
+        for (int xi = G - R.n_express; xi < G && !rc2; xi++) rc2 = service(xi, progressed);
+        for (int gi = 0; gi < G - R.n_express && !rc2; gi++) {
+            bool p = false;
+            rc2 = service(gi, p);
+            if (p) {
+                progressed = true;
+                for (int xi = G - R.n_express; xi < G && !rc2; xi++) rc2 = service(xi, progressed);
+            }
+        }
+        bool any = false;
+        for (int gi = 0; gi < G; gi++) any = any || h->groups[gi]->in_flight;
+        if (!any) break;
+        if (!progressed) std::this_thread::yield();
     }
-    if (!rc2 && R.next < pending.size()) rc2 = fail(OI_ERR_NOMEM, "run_lockstep: scratch arena too small for one cell");
+    if (!rc2 && (R.next < pending.size() || !R.express_pending.empty()))
+        rc2 = fail(OI_ERR_NOMEM, "run_lockstep: scratch arena too small for one cell");
     // join: the handle's stream continues after every group
     for (int gi = 0; gi < G; gi++) {
         cudaEventRecord(h->groups[gi]->done, h->groups[gi]->st);

@@ -189,10 +189,26 @@ def test_engines_and_groupings_bit_identical(small_day):
     cells = np.linspace(0, len(d.X) - 1, 30).round().astype(int)
     h = oi.Handle(0)
     h.set_observations(d.x_train, d.y_train, d.t_train, d.z); h.set_cells(d.X[cells]); h.gather_neighbours(d.radius_km * 1000.0)
+    import os
     ref = None
     for kw in (dict(engine=0, n_groups=1), dict(engine=0, n_groups=8), dict(engine=0, n_groups=3, max_active=7),
+               dict(engine=0, n_groups=4, express=(2, 5, 3)), dict(engine=0, n_groups=2, nograph=True),
                dict(engine=1, group_size=1), dict(engine=1, group_size=3, evals_per_launch=5), dict(engine=1, group_size=8)):
-        h.run(h.make_params(d.radius_km * 1000.0, d.T_mid, d.mean, d.x0, mode=0, **kw))
+        kw = dict(kw)
+        ex = kw.pop("express", None)
+        if kw.pop("nograph", False):     # the first configurations replay CUDA graphs (batches <= 32 cells); this one does not
+            os.environ["OI_GRAPH_MAX"] = "0"
+        if ex:   # force the express-lane hand-over (lanes, after-iterations, lane capacity) on this tiny problem
+            os.environ.update(OI_EXPRESS=str(ex[0]), OI_EXPRESS_AFTER=str(ex[1]), OI_EXPRESS_CAP=str(ex[2]))
+        try:
+            h.run(h.make_params(d.radius_km * 1000.0, d.T_mid, d.mean, d.x0, mode=0, **kw))
+        finally:
+            for k in ("OI_EXPRESS", "OI_EXPRESS_AFTER", "OI_EXPRESS_CAP", "OI_GRAPH_MAX"):
+                os.environ.pop(k, None)
+        if ex:
+            assert h.stats()["n_express_cells"] > 0
+        if ref is None:
+            assert h.stats()["n_graph_launches"] > 0
         r = h.get_results()
         if ref is None:
             ref = r

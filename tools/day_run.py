@@ -24,6 +24,8 @@ if st["launches_persistent"]:
     cyc = st["cycles_phase"]; tot = sum(cyc) or 1
     print("persistent launches", st["launches_persistent"], "phase shares (build, chol, scale, fwd+trtri, alpha, lauum, finalize, idle):",
           [round(c / tot, 3) for c in cyc])
+print("graph captures", st["n_graph_captures"], "graph launches", st["n_graph_launches"], "ms_graph", round(st["ms_graph"], 1))
+print("express cells", st["n_express_cells"], "iterations", st["n_iterations"], "launches", st["n_launches"])
 print("nfev mean", res["nfev"].mean(), "max", res["nfev"].max(), "status hist", np.bincount(res["status"]))
 print("n mean", res["n"].mean(), "out finite frac", np.isfinite(res["out"][:, 0]).mean())
 np.save("gpurun_out/day_stripe_out.npy", res["out"])
