@@ -217,3 +217,48 @@ def test_engines_and_groupings_bit_identical(small_day):
             assert np.array_equal(r["out"], ref["out"], equal_nan=True), kw
             assert np.array_equal(r["nfev"], ref["nfev"]) and np.array_equal(r["status"], ref["status"]), kw
     h.close()
+
+
+def test_ragged_block_edges_and_empty_cells():
+    """Cells whose observation counts sit on the edges of the 64-row blocks and 16-wide DMMA chunks
+    (n = 1, 2, 15..17, 63..65, 127..129, 191..193) plus cells with no observation at all: NLML, gradient and
+    the posterior against the CPU oracle within 1e-9; empty cells give the NaN tuple and status NO_OBS."""
+    import optimalinterpolation_b200 as oi
+    from oracle.gpr_oracle import nlml_grad, predict
+    rng = np.random.default_rng(11)
+    sizes = [1, 2, 15, 16, 17, 63, 64, 65, 127, 128, 129, 191, 192, 193, 0, 0]
+    # every cell gets its own cluster of observations, far (10 000 km apart) from every other cluster
+    xs, ys, ts, zs, X = [], [], [], [], []
+    for k, n in enumerate(sizes):
+        cx, cy = 1.0e7 * k, -2.0e7 * (k % 3)
+        X.append([cx, cy])
+        r = 2.9e5 * np.sqrt(rng.uniform(0, 1, n)); th = rng.uniform(0, 2 * np.pi, n)
+        xs.append(cx + r * np.cos(th)); ys.append(cy + r * np.sin(th))
+        ts.append(rng.integers(0, 9, n).astype(float))
+        zs.append(0.1 + 0.05 * np.sin(xs[-1] / 2e5) + 0.04 * rng.standard_normal(n))
+    x, y, t, z = map(np.concatenate, (xs, ys, ts, zs))
+    perm = rng.permutation(len(x)); x, y, t, z = x[perm], y[perm], t[perm], z[perm]
+    X = np.array(X); mean = 0.1
+    h = oi.Handle(0)
+    h.set_observations(x, y, t, z); h.set_cells(X)
+    counts = h.gather_neighbours(300000.0)
+    assert list(counts) == sizes
+    hyp = np.log([2.15e5, 1.40e5, 21.0, 0.0279, 0.00346, 0.1])
+    nlz, grad = h.nlml_grad(hyp, mean)
+    hn = np.tile(np.exp(hyp[:5]), (len(sizes), 1))
+    h.run(h.make_params(300000.0, 4.0, mean, list(hyp), mode=1), hn)
+    res = h.get_results()
+    offsets, indices = h.get_neighbours()
+    for k, n in enumerate(sizes):
+        if n == 0:
+            assert np.isnan(nlz[k]) and np.isnan(res["out"][k]).all() and res["status"][k] == 4
+            continue
+        ID = indices[offsets[k]:offsets[k + 1]]
+        inp = np.c_[x[ID], y[ID], t[ID]]
+        f, g = nlml_grad(hyp, inp, z[ID], np.ones(n) * mean)
+        assert abs(nlz[k] - f) <= 1e-9 * max(abs(f), 1.0), (n, nlz[k], f)
+        assert np.abs(grad[k] - g).max() <= 1e-9 * max(np.abs(g).max(), 1.0), (n, grad[k], g)
+        fs, sfs2, lZ = predict(inp, z[ID], mean, np.array([[X[k, 0], X[k, 1], 4.0]]), list(hn[k, :3]), hn[k, 3], hn[k, 4])
+        got = res["out"][k]
+        assert abs(got[0] - fs) <= 1e-9 * abs(fs) and abs(got[1] - sfs2) <= 1e-9 * abs(sfs2) and abs(got[2] - lZ) <= 1e-9 * max(abs(lZ), 1.0), (n, got[:3], (fs, sfs2, lZ))
+    h.close()
