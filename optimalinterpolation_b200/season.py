@@ -1,0 +1,87 @@
+"""Day setup and season loop around the batched GP path, mirroring GPR_CS2S3.py:201-246.
+
+The reference script processes ONE hard-coded day (``day = 1``, :211): it slices the ``T``-day window out of the
+season's gridded observations (:213), flattens it stream-major / day-major / row-major into ``x_train, y_train,
+t_train, z`` (:223-241), takes the ice cells of the middle day (:214, :243-244) and a prior mean (:212), and then
+runs both passes.  ``run_season`` repeats exactly that setup for a list of days on one resident GPU handle.
+Everything here is O(grid) host work; a day's flattened observations are ~1 MB, so keeping the whole season
+resident on the device would buy nothing - the window is rebuilt on the host and uploaded by ``oi_gpr_day``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .gpr import GPRDay, Handle
+from .postprocess import assemble, two_pass
+
+
+def flatten_window(obs: np.ndarray, x: np.ndarray, y: np.ndarray, day: int, T: int = 9):
+    """``sat = obs[:, :, :, day:day+T]`` (:213) flattened as at :223-241.
+
+    obs: (ny, nx, n_streams, n_days) gridded observations, NaN where empty; x, y: (ny, nx) cell coordinates.
+    Returns x_train, y_train, t_train (day index inside the window, 0..T-1), z.
+    """
+    sat = obs[:, :, :, day:day + T]
+    xs, ys, ts, zs = [], [], [], []
+    for stream in range(sat.shape[2]):            # x1.., x2.., x3.., x4.. concatenated (:238-241)
+        for d in range(sat.shape[3]):             # for day in range(sat.shape[3]) (:227)
+            field = sat[:, :, stream, d]
+            idx = np.where(~np.isnan(field))      # row-major (:228-231)
+            xs.append(x[idx]); ys.append(y[idx])
+            ts.append(np.ones(idx[0].size) * d)
+            zs.append(field[idx])
+    return (np.concatenate(xs).astype(np.float64), np.concatenate(ys).astype(np.float64),
+            np.concatenate(ts).astype(np.float64), np.concatenate(zs).astype(np.float64))
+
+
+def day_inputs(obs, sie_mask, x, y, day: int, T: int = 9, prior_mean=None) -> dict:
+    """The module globals of GPR_CS2S3.py:207-246 for one day index (the interpolated day is day + T//2).
+
+    prior_mean: float, or callable(day) -> float.  The reference uses the mean of a separate CS2 first-year-ice
+    product over the previous 9 days (:212, data not shipped); the default here is the rounded mean of the
+    window's own observations, as in the synthetic generator.
+    """
+    T_mid = T // 2
+    x_train, y_train, t_train, z = flatten_window(obs, x, y, day, T)
+    SIE = sie_mask[:, :, day + T_mid]                                    # :214
+    ids = np.where(~np.isnan(SIE))                                       # :243
+    X = np.array([x[ids], y[ids]]).T.astype(np.float64).copy()           # :244
+    if prior_mean is None:
+        mean = float(np.round(np.mean(z), 3)) if z.size else 0.0
+    elif callable(prior_mean):
+        mean = float(prior_mean(day))
+    else:
+        mean = float(prior_mean)
+    return dict(x_train=x_train, y_train=y_train, t_train=t_train, z=z, X=X, ids=ids, SIE=SIE, mean=mean,
+                T=T, T_mid=T_mid)
+
+
+def run_season(obs, sie_mask, x, y, days, dates=None, grid_res: float = 25, T: int = 9, radius: float = 300,
+               x0=None, prior_mean=None, smooth_pass: bool = True, device: int = 0, handle: Handle | None = None,
+               **run_kw) -> dict:
+    """Both passes (or pass 1 only) for every day index in ``days`` on one GPU handle.
+
+    Returns one dict with the reference's per-date keys (``<date>_interp``, ``<date>_ell_x_smth``, ...,
+    GPR_CS2S3.py:290-297, :303-307, :333-334); ``dates[day + T//2]`` names a day (default: the index)."""
+    if x0 is None:
+        x0 = [np.log(grid_res * 1000), np.log(grid_res * 1000), np.log(1.), np.log(1.), np.log(1.), np.log(.1)]   # :217
+    own = handle is None
+    handle = handle or Handle(device)
+    out = {}
+    try:
+        for day in days:
+            g = day_inputs(obs, sie_mask, x, y, day, T, prior_mean)
+            date = str(dates[day + g["T_mid"]]) if dates is not None else str(day + g["T_mid"])
+            gd = GPRDay(g["x_train"], g["y_train"], g["t_train"], g["z"], g["X"], radius, g["mean"], g["T_mid"], x0,
+                        handle=handle)
+            if smooth_pass:
+                res = two_pass(gd, g["ids"], g["SIE"].shape, g["SIE"], date=date, grid_res=grid_res, T=T, **run_kw)
+                res[date + "_diagnostics"] = res.pop("_diagnostics")
+            else:
+                r1 = gd.run(opt=True, **run_kw)
+                res = assemble(r1["out"], g["ids"], g["SIE"].shape, date)
+            out.update(res)
+    finally:
+        if own:
+            handle.close()
+    return out

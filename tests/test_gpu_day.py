@@ -134,3 +134,39 @@ def test_two_pass_small_day(small_day, small_oracle):
     for c in range(0, len(d.X), 25):
         ref = o.gpr3d(c, hypers=[ell[c, 0], ell[c, 1], ell[c, 2], sf2[c], sn2[c]], sort=True)
         assert abs(fs[c] - ref[0]) <= 1e-9 * abs(ref[0]) and abs(er[c] - ref[1]) <= 1e-8 * abs(ref[1]), c
+
+
+def test_config5_large_cell_vs_oracle():
+    """BASELINE.json configs[4]: 12.5 km lattice, r = 500 km, thousands of observations per cell (here one cell with
+    n ~ 3300, N = 52 blocks): NLML, gradient and posterior within 1e-9 of the CPU oracle; the neighbour set is exact."""
+    import optimalinterpolation_b200 as oi
+    from oracle.gpr_oracle import nlml_grad, predict, neighbours_brute
+    rng = np.random.default_rng(12)
+    side = 100                                           # 12.5 km lattice sites around the cell, ~8 % of site-days observed
+    jj, ii = np.meshgrid(np.arange(-side, side + 1), np.arange(-side, side + 1))
+    xs, ys, ts = [], [], []
+    for day in range(9):
+        hit = rng.uniform(size=jj.shape) < 0.073
+        xs.append(12500.0 * jj[hit]); ys.append(12500.0 * ii[hit]); ts.append(np.full(hit.sum(), float(day)))
+    x, y, t = map(np.concatenate, (xs, ys, ts))
+    z = 0.1 + 0.06 * np.sin(x / 3e5) * np.cos(y / 2.5e5) + 0.003 * (t - 4) + 0.04 * rng.standard_normal(x.size)
+    X = np.array([[0.0, 0.0]]); mean = float(np.round(z.mean(), 3))
+    h = oi.Handle(0)
+    h.set_observations(x, y, t, z); h.set_cells(X)
+    n = int(h.gather_neighbours(500000.0)[0])
+    assert 2500 < n < 5000
+    offsets, indices = h.get_neighbours()
+    assert np.array_equal(indices, neighbours_brute(x, y, X[0], 500000.0))
+    hyp = np.log([3.0e5, 2.2e5, 15.0, 0.02, 0.004, 0.1])
+    nlz, grad = h.nlml_grad(hyp, mean)
+    inp = np.c_[x[indices], y[indices], t[indices]]
+    f, g = nlml_grad(hyp, inp, z[indices], np.ones(n) * mean)
+    assert abs(nlz[0] - f) <= 1e-9 * abs(f), (n, nlz[0], f)
+    assert np.abs(grad[0] - g).max() <= 1e-9 * np.abs(g).max(), (grad[0], g)
+    hn = np.exp(hyp[:5])[None, :]
+    h.run(h.make_params(500000.0, 4.0, mean, list(hyp), mode=1), hn)
+    got = h.get_results()["out"][0]
+    fs, sfs2, lZ = predict(inp, z[indices], mean, np.array([[0.0, 0.0, 4.0]]), list(hn[0, :3]), hn[0, 3], hn[0, 4])
+    assert abs(got[0] - fs) <= 1e-9 * abs(fs) and abs(got[1] - sfs2) <= 1e-9 * abs(sfs2) and abs(got[2] - lZ) <= 1e-9 * abs(lZ)
+    print("config-5 cell: n =", n, "rel err nlZ", abs(nlz[0] - f) / abs(f), "grad", np.abs(grad[0] - g).max() / np.abs(g).max())
+    h.close()

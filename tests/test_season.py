@@ -1,0 +1,63 @@
+"""Season/day setup (GPR_CS2S3.py:201-246): CPU checks of the window flattening, GPU check of the season loop."""
+import numpy as np
+import pytest
+
+from optimalinterpolation_b200.synthetic import make_day
+
+
+def _small_season(T_total=11):
+    d = make_day(n_side=40, ice_radius_cells=14.0, centre=(20, 20), radius_km=100.0, tracks_per_day=4, seed=5,
+                 s3_hole_cells=4.0, cs2_hole_cells=1.0, keep_sat=True, T=T_total)
+    res = 25000.0
+    jj, ii = np.meshgrid(np.arange(40), np.arange(40))
+    x, y = res * jj.astype(float), res * ii.astype(float)
+    sie = np.full((40, 40, T_total), np.nan)
+    sie[d.ids[0], d.ids[1], :] = 1.0
+    sie[d.ids[0][::7], d.ids[1][::7], 6] = np.nan          # the ice mask changes from day to day
+    return d.sat, sie, x, y
+
+
+def test_flatten_window_matches_reference_loop():
+    from optimalinterpolation_b200.season import flatten_window, day_inputs
+    obs, sie, x, y = _small_season()
+    for day in (0, 2):
+        sat = obs[:, :, :, day:day + 9]                     # GPR_CS2S3.py:213
+        # the reference's loop, GPR_CS2S3.py:223-241
+        xs = [[] for _ in range(4)]; ys = [[] for _ in range(4)]; ts = [[] for _ in range(4)]; zs = [[] for _ in range(4)]
+        for dd in range(sat.shape[3]):
+            for s in range(4):
+                ids = np.where(~np.isnan(sat[:, :, s, dd]))
+                xs[s].extend(x[ids]); ys[s].extend(y[ids]); ts[s].extend(np.ones(np.shape(ids)[1]) * dd)
+                zs[s].extend(sat[:, :, s, dd][ids])
+        xt, yt, tt, z = flatten_window(obs, x, y, day, 9)
+        assert np.array_equal(np.concatenate(xs), xt) and np.array_equal(np.concatenate(ys), yt)
+        assert np.array_equal(np.concatenate(ts), tt) and np.array_equal(np.concatenate(zs), z)
+        g = day_inputs(obs, sie, x, y, day, 9)
+        ids = np.where(~np.isnan(sie[:, :, day + 4]))       # :214, :243-244
+        assert np.array_equal(g["X"], np.array([x[ids], y[ids]]).T) and g["T_mid"] == 4
+        assert g["mean"] == float(np.round(np.mean(z), 3))
+    assert day_inputs(obs, sie, x, y, 0, 9, prior_mean=0.25)["mean"] == 0.25
+    assert day_inputs(obs, sie, x, y, 2, 9, prior_mean=lambda d: 0.1 * d)["mean"] == 0.2
+
+
+@pytest.mark.gpu
+def test_run_season_equals_day_by_day():
+    """Two days on one resident handle give exactly what two independent GPRDay runs give (handle reuse across
+    days with different observation and cell counts must not leak state)."""
+    import optimalinterpolation_b200 as oi
+    from optimalinterpolation_b200.season import run_season, day_inputs
+    from optimalinterpolation_b200.postprocess import two_pass
+    obs, sie, x, y = _small_season()
+    season = run_season(obs, sie, x, y, days=[0, 2], radius=100, dates=[f"201901{d:02d}" for d in range(1, 12)])
+    for day in (0, 2):
+        g = day_inputs(obs, sie, x, y, day, 9)
+        date = f"201901{day + 5:02d}"
+        gd = oi.GPRDay(g["x_train"], g["y_train"], g["t_train"], g["z"], g["X"], 100, g["mean"], g["T_mid"],
+                       [np.log(25000.), np.log(25000.), 0., 0., 0., np.log(.1)])
+        ref = two_pass(gd, g["ids"], g["SIE"].shape, g["SIE"], date=date)
+        gd.handle.close()
+        for k, v in ref.items():
+            if k == "_diagnostics":
+                continue
+            assert np.array_equal(season[k], v, equal_nan=True), k
+        assert np.isfinite(season[date + "_interp_smth"][g["ids"]]).mean() > 0.9
