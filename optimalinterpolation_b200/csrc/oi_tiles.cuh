@@ -482,6 +482,8 @@ __device__ __forceinline__ void cell_fwd(const OiSlot& s, const OiCellArrays& ca
 #pragma unroll
             for (int q = 0; q < 8; q++) { a0[q] = 0.0; a1[q] = 0.0; }
             const double* Lrow = s.M + (long long)(kc + vw * 8) * ld;
+            // unrolled so that several iterations' loads (8 rows + x per iteration) are in flight; the FMAs keep their order
+#pragma unroll 4
             for (int c = lane; c < kc; c += 32) {
                 double x0 = __ldcg(&tv[c]), x1 = pred ? __ldcg(&vv[c]) : 0.0;
 #pragma unroll
@@ -648,6 +650,7 @@ __device__ __forceinline__ void rows_alpha(const OiSlot& s, int rb) {
 #pragma unroll
         for (int q = 0; q < 8; q++) a[q] = 0.0;
         const double* Urow = s.M + (long long)r0 * ld;
+#pragma unroll 4
         for (int c = rb * NB + lane; c < s.npad; c += 32) {
             double x = __ldcg(&tv[c]);
 #pragma unroll
