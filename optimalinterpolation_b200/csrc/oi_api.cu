@@ -72,6 +72,7 @@ static size_t slot_bytes(int n) {
     b += align_up(N * OI_TILE * 8, 256);
     b += align_up(3 * npad * 8, 256);
     b += align_up((N + 8 + 5 * N * (N + 1) / 2) * 8, 256);
+    b += align_up(N * (N + 1) / 2 * 2 * OI_TILE * 8, 256);      // Q and exp(-Q) tiles
     return b;
 }
 
@@ -369,6 +370,7 @@ struct LockstepRun {
             s.Dinv = (double*)(g.arena + off); off += align_up((size_t)N * OI_TILE * 8, 256);
             s.vec = (double*)(g.arena + off); off += align_up((size_t)3 * npad * 8, 256);
             s.part = (double*)(g.arena + off); off += align_up((size_t)(N + 8 + 5 * N * (N + 1) / 2) * 8, 256);
+            s.QE = (double*)(g.arena + off); off += align_up((size_t)N * (N + 1) / 2 * 2 * OI_TILE * 8, 256);
             s.fail = g.d_fail + a;
             s.pt_off = h->h_offsets[c];
             s.cell = c; s.n = n; s.npad = npad; s.N = N; s.n16 = (n + 15) / 16 * 16; s.pad_ = 0;

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(OI_THREADS) k_build(const OiSlot* __restrict__
     if (row >= 0) { i = row; j = blockIdx.x; }      // one launch per block row (exact grids for big batches)
     else tile_ij(blockIdx.x, i, j);
     if (i >= s.N) return;
-    tile_build(s, ca, pk, i, j, smem);
+    tile_build(s, ca, pk, i, j, ca.phase[s.cell] != OI_PH_PREDICT, smem);
 }
 
 __global__ void __launch_bounds__(OI_THREADS, 3) k_chol_update(const OiSlot* __restrict__ slots, int k) {
@@ -243,7 +243,8 @@ __global__ void __launch_bounds__(OI_THREADS, 3) k_gp_persistent(OiPersist P, Oi
             s.M = (double*)(scratch + off); off += ((size_t)npad * npad * 8 + 255) & ~(size_t)255;
             s.Dinv = (double*)(scratch + off); off += ((size_t)N * OI_TILE * 8 + 255) & ~(size_t)255;
             s.vec = (double*)(scratch + off); off += ((size_t)3 * npad * 8 + 255) & ~(size_t)255;
-            s.part = (double*)(scratch + off);
+            s.part = (double*)(scratch + off); off += ((size_t)(N + 8 + 5 * N * (N + 1) / 2) * 8 + 255) & ~(size_t)255;
+            s.QE = (double*)(scratch + off);
             s.fail = P.fail + grp;
             s.pt_off = w.pt_off; s.cell = w.cell; s.n = w.n; s.npad = npad; s.N = N; s.n16 = (w.n + 15) / 16 * 16; s.pad_ = 0;
         }
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(OI_THREADS, 3) k_gp_persistent(OiPersist P, Oi
             if (phase == OI_PH_DONE) break;
             const bool pred = phase == OI_PH_PREDICT;
             // ---- covariance ----
-            for (int t = r; t < ntl; t += gs) { int i, j; tile_ij(t, i, j); tile_build(s, ca, pk, i, j, smem); }
+            for (int t = r; t < ntl; t += gs) { int i, j; tile_ij(t, i, j); tile_build(s, ca, pk, i, j, !pred, smem); }
             group_barrier(ctl, epoch, gs);
             PT_MARK(PT_BUILD);
             // ---- blocked left-looking Cholesky ----

@@ -78,7 +78,8 @@ __device__ __forceinline__ double pair_Q(double dx, double dy, double dt) {
 // (GPR_CS2S3.py:93-94, :126); padding rows/cols are identity so every later tile is full.
 // smem: 6*NB doubles.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tile_build(const OiSlot& s, const OiCellArrays& ca, const OiPacked& pk, int i, int j, double* smem) {
+__device__ __forceinline__ void tile_build(const OiSlot& s, const OiCellArrays& ca, const OiPacked& pk, int i, int j, bool want_qe,
+                                           double* smem) {
     const int tid = threadIdx.x;
     if (i == 0 && tid == 0) *s.fail = 0;
     double(*ru)[NB] = (double(*)[NB])smem;
@@ -101,20 +102,23 @@ __device__ __forceinline__ void tile_build(const OiSlot& s, const OiCellArrays& 
     }
     __syncthreads();
     const long long ld = s.npad;
+    double* qe = s.QE + 2 * (long long)OI_TILE * (i * (i + 1) / 2 + j);
 #pragma unroll 4
     for (int e = 0; e < OI_TILE / OI_THREADS; e++) {
         int idx = tid + e * OI_THREADS;
         int r = idx / NB, c = idx % NB;
         int gi = i * NB + r, gj = j * NB + c;
-        double val;
+        double val, Q = 0.0, E = 1.0;
         if (gi >= s.n || gj >= s.n) val = (gi == gj) ? 1.0 : 0.0;
         else if (gi == gj) val = sf2 + sn2;
         else {
-            double Q = pair_Q(ru[0][r] - cu[0][c], ru[1][r] - cu[1][c], ru[2][r] - cu[2][c]);
+            Q = pair_Q(ru[0][r] - cu[0][c], ru[1][r] - cu[1][c], ru[2][r] - cu[2][c]);
+            E = exp(-Q);
             // + np.eye(n)*sn2 off the diagonal is +0*sn2: NaN when sn2 overflowed (GPR_CS2S3.py:126)
-            val = sf2 * ((1.0 + Q) * exp(-Q)) + 0.0 * sn2;
+            val = sf2 * ((1.0 + Q) * E) + 0.0 * sn2;
         }
         s.M[(long long)gi * ld + gj] = val;
+        if (want_qe) { qe[idx] = Q; qe[OI_TILE + idx] = E; }
     }
 }
 
@@ -670,7 +674,7 @@ __device__ __forceinline__ void rows_alpha(const OiSlot& s, int rb) {
 // GPR_CS2S3.py:130-138:  Qm = K^-1 - alpha alpha^T,
 //   S_theta = sum Qm * q_theta^2 exp(-Q)   (theta = x, y, t)      S_3 = sum Qm * (1+Q) exp(-Q)
 //   S_4 = tr(Qm)
-// dK/dtheta is recomputed from the coordinates in registers; K^-1 is never stored.
+// dK/dtheta is rebuilt in registers from the coordinates and the stored Q, exp(-Q) tiles; K^-1 is never stored.
 // Each tile writes five partial sums; off-diagonal tiles count twice (symmetry).  smem: PIPE_BYTES.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tile_lauum_trace(const OiSlot& s, const OiCellArrays& ca, const OiPacked& pk, int i, int j, double* smem) {
@@ -703,37 +707,41 @@ __device__ __forceinline__ void tile_lauum_trace(const OiSlot& s, const OiCellAr
                            return SubRange{0, mh, 0, nh};
                        });
     }
-    // per-point data of the 64 rows and 64 cols: u (3), v (3), alpha (raw values were fetched before the K loop)
-    double(*P)[7][NB] = (double(*)[7][NB])smem;    // P[0]=rows, P[1]=cols
-    double(*red)[4] = (double(*)[4])(smem + 2 * 7 * NB);   // [5][4]
+    // per-point data of the 64 rows and 64 cols: scaled coordinates for q_theta (3) and alpha (raw values were fetched
+    // before the K loop); Q and exp(-Q) of every pair come from the tile the covariance build left in s.QE
+    double(*P)[4][NB] = (double(*)[4][NB])smem;    // P[0]=rows, P[1]=cols
+    double(*red)[4] = (double(*)[4])(smem + 2 * 4 * NB);   // [5][4]
     {
         int which = tid / NB, q = tid % NB;        // 128 threads: rows then cols
         double x = praw[0], y = praw[1], t = praw[2], a = praw[3];
-        P[which][0][q] = (ROOT3 * x) / h0; P[which][1][q] = (ROOT3 * y) / h1; P[which][2][q] = (ROOT3 * t) / h2;
         // np.sqrt(3.)*(x[:,theta]/ell[theta])  (GPR_CS2S3.py:97): divide, then multiply
-        P[which][3][q] = ROOT3 * (x / h0); P[which][4][q] = ROOT3 * (y / h1); P[which][5][q] = ROOT3 * (t / h2);
-        P[which][6][q] = a;
+        P[which][0][q] = ROOT3 * (x / h0); P[which][1][q] = ROOT3 * (y / h1); P[which][2][q] = ROOT3 * (t / h2);
+        P[which][3][q] = a;
     }
     __syncthreads();
+    const double* qe = s.QE + 2 * (long long)OI_TILE * (i * (i + 1) / 2 + j);
     double S[5] = {0, 0, 0, 0, 0};
 #pragma unroll
     for (int mb = 0; mb < 4; mb++) {
         const int r = FRAG_ROW(wm, mb, lane), gi = i * NB + r;
 #pragma unroll
         for (int nb = 0; nb < 4; nb++) {
+            const int c0 = FRAG_COL(wn, nb, lane);
+            if (gi >= s.n || j * NB + c0 > gi) continue;     // padding row, or both columns above the diagonal
+            const double2 Q2 = __ldcg((const double2*)&qe[r * NB + c0]);
+            const double2 E2 = __ldcg((const double2*)&qe[OI_TILE + r * NB + c0]);
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-                const int c = FRAG_COL(wn, nb, lane) + e, gj = j * NB + c;
-                if (gi < s.n && gj < s.n && gj <= gi) {
-                    double Qm = fma(-P[0][6][r], P[1][6][c], acc[mb][nb][e]);
+                const int c = c0 + e, gj = j * NB + c;
+                if (gj < s.n && gj <= gi) {
+                    double Qm = fma(-P[0][3][r], P[1][3][c], acc[mb][nb][e]);
                     if (gi == gj) {
                         // Q = 0: dK_theta = 0, K = sf2
                         S[3] += Qm; S[4] += Qm;
                     } else {
                         Qm *= 2.0;          // (gi, gj) and (gj, gi): K^-1, alpha alpha^T and dK are symmetric
-                        double Q = pair_Q(P[0][0][r] - P[1][0][c], P[0][1][r] - P[1][1][c], P[0][2][r] - P[1][2][c]);
-                        double E = exp(-Q);
-                        double qx = P[0][3][r] - P[1][3][c], qy = P[0][4][r] - P[1][4][c], qt = P[0][5][r] - P[1][5][c];
+                        const double Q = e ? Q2.y : Q2.x, E = e ? E2.y : E2.x;
+                        double qx = P[0][0][r] - P[1][0][c], qy = P[0][1][r] - P[1][1][c], qt = P[0][2][r] - P[1][2][c];
                         S[0] = fma(Qm, qx * qx * E, S[0]);
                         S[1] = fma(Qm, qy * qy * E, S[1]);
                         S[2] = fma(Qm, qt * qt * E, S[2]);

@@ -15,6 +15,8 @@ struct OiSlot {
     double* Dinv;     // N x (64x64) row-major inverses of the diagonal Cholesky blocks
     double* vec;      // 3*npad: t = L^-1 r | v = L^-1 k* | alpha = K^-1 r
     double* part;     // [0,N) logdet parts | [N,N+8) scalars (t.t, v.t, v.v) | [N+8, ..) 5 trace partials per tile
+    double* QE;       // per lower tile (i,j): 64x64 Q = scaled distances, then 64x64 E = exp(-Q), written by the covariance
+                      // build and re-read by the trace epilogue (trades FP64-pipe work, shared with DMMA, for idle HBM bandwidth)
     int* fail;        // set when a Cholesky pivot is <= 0 or NaN (np.linalg.LinAlgError in the reference)
     long long pt_off; // offset of this cell's points in the packed (CSR-ordered) coordinate arrays
     int cell, n, npad, N;

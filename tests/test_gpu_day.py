@@ -170,3 +170,31 @@ def test_config5_large_cell_vs_oracle():
     assert abs(got[0] - fs) <= 1e-9 * abs(fs) and abs(got[1] - sfs2) <= 1e-9 * abs(sfs2) and abs(got[2] - lZ) <= 1e-9 * abs(lZ)
     print("config-5 cell: n =", n, "rel err nlZ", abs(nlz[0] - f) / abs(f), "grad", np.abs(grad[0] - g).max() / np.abs(g).max())
     h.close()
+
+
+def test_fit_full_size_large_sample(day):
+    """160 cells of the full day (n <= 1100, stratified) fitted by the reference path on the CPU
+    (tests/golden/make_day_fit_sample_large.py) vs the GPU: BASELINE.json's tolerance is |d fs| <= 1 mm and
+    NLML within 1e-6 relative (or better).  The optimiser's end point is chaotic at round-off level for a few
+    cells, so the gate is 97 %; the measured fractions are printed."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "day_fit_sample_large.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/day_fit_sample_large.npz not generated")
+    import optimalinterpolation_b200 as oi
+    g = np.load(path)
+    cells = g["cells"]
+    gd = oi.GPRDay(day.x_train, day.y_train, day.t_train, day.z, day.X[cells], day.radius_km, day.mean, day.T_mid, day.x0)
+    res = gd.run(opt=True)
+    out, ref = res["out"], g["out"]
+    assert np.array_equal(res["n"], g["n"])
+    nan_gpu, nan_ref = np.isnan(out[:, 0]), np.isnan(ref[:, 0])
+    both = ~nan_gpu & ~nan_ref
+    dfs = np.abs(out[both, 0] - ref[both, 0]) * 1e3
+    dsd = np.abs(out[both, 1] - ref[both, 1]) * 1e3
+    rel = (out[both, 2] - ref[both, 2]) / np.abs(ref[both, 2])
+    print(f"large fit sample: {both.sum()} finite cells (n {g['n'].min()}..{g['n'].max()}), NaN mismatch {(nan_gpu != nan_ref).sum()}; "
+          f"|dfs| mm median {np.median(dfs):.2e} p99 {np.percentile(dfs, 99):.3e} max {dfs.max():.3e}, <=1mm {np.mean(dfs <= 1.0):.4f}; "
+          f"|d std| mm max {dsd.max():.3e}; lZ >= ref*(1-1e-6): {np.mean(rel > -1e-6):.4f}, |rel lZ| max {np.abs(rel).max():.2e}; "
+          f"nfev gpu {res['nfev'].mean():.0f} ref {g['nfev'].mean():.0f}")
+    assert (nan_gpu != nan_ref).sum() <= 2
+    assert np.mean(dfs <= 1.0) >= 0.97 and np.mean(rel > -1e-6) >= 0.97
