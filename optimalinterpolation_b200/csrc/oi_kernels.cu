@@ -98,7 +98,14 @@ __global__ void __launch_bounds__(OI_THREADS) k_build(const OiSlot* __restrict__
     tile_build(s, ca, pk, i, j, ca.phase[s.cell] != OI_PH_PREDICT, smem);
 }
 
-__global__ void __launch_bounds__(OI_THREADS, 3) k_chol_update(const OiSlot* __restrict__ slots, int k) {
+#ifdef OI_EXP_ALIAS_DIAG
+#define OI_UPD_MINB 4
+#define OI_UPD_SMEM OI_SMEM_PIPE
+#else
+#define OI_UPD_MINB 3
+#define OI_UPD_SMEM OI_SMEM_BYTES
+#endif
+__global__ void __launch_bounds__(OI_THREADS, OI_UPD_MINB) k_chol_update(const OiSlot* __restrict__ slots, int k) {
     extern __shared__ __align__(16) double smem[];
     const OiSlot s = slots[blockIdx.y];
     const int i = k + blockIdx.x;
@@ -365,7 +372,7 @@ void oi_launch_build(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, Oi
 }
 void oi_launch_chol_update(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int k, cudaStream_t st) {
     set_attrs();
-    k_chol_update<<<dim3(k == 0 ? 1 : Nmax - k, cnt_gt[k]), OI_THREADS, OI_SMEM_BYTES, st>>>(slots, k);
+    k_chol_update<<<dim3(k == 0 ? 1 : Nmax - k, cnt_gt[k]), OI_THREADS, OI_UPD_SMEM, st>>>(slots, k);
 }
 void oi_launch_chol_panel(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int k, cudaStream_t st) {
     set_attrs();

@@ -284,7 +284,9 @@ __device__ __forceinline__ void diag_factor_invert(double* T, double* W, double*
             }
         }
         __syncthreads();
+#ifndef OI_EXP_ALIAS_DIAG
         if (*s_bad) return;
+#endif
         // panel: L_ij = A_ij * X_jj^T  (i > j)
         for (int i = j + 1 + warp; i < 8; i += 4) {
             double c2[2] = {0.0, 0.0};
@@ -382,9 +384,16 @@ __device__ __forceinline__ void tile_chol_update(const OiSlot& s, int i, int k, 
     }
     // ---- diagonal tile: T = A_kk - acc, factor + invert in shared memory ----
     double* T = smem;                    // [64][TS]  A_kk -> L_kk (lower)
+#ifdef OI_EXP_ALIAS_DIAG
+    // TIMING EXPERIMENT ONLY (wrong numbers): W aliases T so that the CTA needs 37 KB instead of 72 KB
+    double* W = smem;
+    double* sc = smem + NB * TS + warp * 64;
+    int* s_bad = (int*)(smem + NB * TS + 4 * 64);
+#else
     double* W = smem + NB * TS;          // [64][TS]  L_kk^-1 (lower, zeros above)
     double* sc = smem + 2 * NB * TS + warp * 64;   // per-warp 8x8 scratch
     int* s_bad = (int*)(smem + 2 * NB * TS + 4 * 64);
+#endif
 #pragma unroll
     for (int mb = 0; mb < 4; mb++)
 #pragma unroll
@@ -397,10 +406,12 @@ __device__ __forceinline__ void tile_chol_update(const OiSlot& s, int i, int k, 
     if (tid == 0) *s_bad = 0;
     __syncthreads();
     diag_factor_invert(T, W, sc, s_bad, tid);
+#ifndef OI_EXP_ALIAS_DIAG
     if (*s_bad) {
         if (tid == 0) *s.fail = 1;
         return;
     }
+#endif
     if (warp == 0) {
         // log-determinant part: sum_i log L_ii of this block (GPR_CS2S3.py:128), fixed order
         double v = log(T[lane * TS + lane]) + log(T[(lane + 32) * TS + lane + 32]);
