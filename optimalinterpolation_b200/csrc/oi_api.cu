@@ -49,7 +49,7 @@ struct oi_handle {
     // lockstep batch
     char* arena = nullptr; size_t arena_bytes = 0;
     OiSlot* d_slots = nullptr; OiSlot* h_slots = nullptr;
-    int *d_slot_phase = nullptr, *h_slot_phase = nullptr, *d_fail = nullptr;
+    int *d_slot_phase = nullptr, *h_slot_phase = nullptr, *d_fail = nullptr, *d_tickets = nullptr;
     int slot_cap = 0;
     cudaEvent_t ev[10]{};
     std::vector<struct OiGroup*> groups;
@@ -73,6 +73,7 @@ static size_t slot_bytes(int n) {
     b += align_up(3 * npad * 8, 256);
     b += align_up((N + 8 + 5 * N * (N + 1) / 2) * 8, 256);
     b += align_up(N * (N + 1) / 2 * 2 * OI_TILE * 8, 256);      // Q and exp(-Q) tiles
+    b += align_up(2 * N * 4, 256);                                // dependency flags of the fused Cholesky
     return b;
 }
 
@@ -125,7 +126,7 @@ extern "C" void oi_destroy(oi_handle* h) {
     cudaFree(h->ox); cudaFree(h->oy); cudaFree(h->ot); cudaFree(h->oz);
     free_cells(h);
     cudaFree(h->indices); cudaFree(h->px); cudaFree(h->py); cudaFree(h->pt); cudaFree(h->pr);
-    cudaFree(h->arena); cudaFree(h->d_slots); cudaFree(h->d_slot_phase); cudaFree(h->d_fail);
+    cudaFree(h->arena); cudaFree(h->d_slots); cudaFree(h->d_slot_phase); cudaFree(h->d_fail); cudaFree(h->d_tickets);
     cudaFreeHost(h->h_slots); cudaFreeHost(h->h_slot_phase);
     free_groups(h);
     cudaFree(h->d_work); cudaFreeHost(h->h_work); cudaFree(h->d_ctl); cudaFree(h->d_pfail); cudaFree(h->d_queue); cudaFree(h->d_acc);
@@ -238,7 +239,7 @@ struct OiGroup {
     cudaEvent_t ev[8]{};            // family boundaries of the iteration in flight
     cudaEvent_t done = nullptr;
     OiSlot *d_slots = nullptr, *h_slots = nullptr;
-    int *d_slot_phase = nullptr, *h_slot_phase = nullptr, *d_fail = nullptr;
+    int *d_slot_phase = nullptr, *h_slot_phase = nullptr, *d_fail = nullptr, *d_ticket = nullptr;
     char* arena = nullptr; size_t arena_bytes = 0, used = 0;
     long long tiles = 0;            // sum of N(N+1)/2 over the active cells (work admitted to the group)
     bool high_prio = false;
@@ -267,6 +268,7 @@ static int ensure_batch_buffers(oi_handle* h, size_t want_arena, int want_slots,
         CK(cudaMallocHost(&h->h_slot_phase, (size_t)want_slots * 4));
         h->slot_cap = want_slots;
     }
+    if (!h->d_tickets) CK(cudaMalloc(&h->d_tickets, 16 * 32 * 4));      // one ticket counter per group, 128 B apart
     while ((int)h->groups.size() < G) {
         OiGroup* g = new OiGroup();
         CK(cudaStreamCreateWithFlags(&g->st, cudaStreamNonBlocking));
@@ -306,15 +308,21 @@ struct LockstepRun {
     long long cell_tiles(int c) const { long long N = (h->h_counts[c] + OI_NB - 1) / OI_NB; return N * (N + 1) / 2; }
 
     int graph_max_A = 0;            // batches up to this many cells replay a captured graph
+    bool fused_chol = false;        // OI_FUSED_CHOL=1: one launch for all block columns (k_chol_fused); measured slower, off
 
     // the kernel chain of one lockstep iteration of group g (timed: with the family boundary events)
     int launch_chain(OiGroup& g, int A, int Nmax, const int* cg, cudaStream_t st, bool timed) {
         if (timed) CK(cudaEventRecord(g.ev[0], st));
         oi_launch_build(g.d_slots, A, Nmax, cg, h->ca, pk, st);
         if (timed) CK(cudaEventRecord(g.ev[1], st));
-        for (int k = 0; k < Nmax; k++) {
-            oi_launch_chol_update(g.d_slots, A, Nmax, cg, k, st);
-            oi_launch_chol_panel(g.d_slots, A, Nmax, cg, k, st);
+        if (fused_chol && Nmax <= OI_MAX_NB) {
+            CK(cudaMemsetAsync(g.d_ticket, 0, 4, st));
+            oi_launch_chol_fused(g.d_slots, A, Nmax, cg, g.d_ticket, st);
+        } else {
+            for (int k = 0; k < Nmax; k++) {
+                oi_launch_chol_update(g.d_slots, A, Nmax, cg, k, st);
+                oi_launch_chol_panel(g.d_slots, A, Nmax, cg, k, st);
+            }
         }
         oi_launch_scale_rows(g.d_slots, A, Nmax, cg, st);
         if (timed) CK(cudaEventRecord(g.ev[2], st));
@@ -371,6 +379,7 @@ struct LockstepRun {
             s.vec = (double*)(g.arena + off); off += align_up((size_t)3 * npad * 8, 256);
             s.part = (double*)(g.arena + off); off += align_up((size_t)(N + 8 + 5 * N * (N + 1) / 2) * 8, 256);
             s.QE = (double*)(g.arena + off); off += align_up((size_t)N * (N + 1) / 2 * 2 * OI_TILE * 8, 256);
+            s.flags = (int*)(g.arena + off); off += align_up((size_t)2 * N * 4, 256);
             s.fail = g.d_fail + a;
             s.pt_off = h->h_offsets[c];
             s.cell = c; s.n = n; s.npad = npad; s.N = N; s.n16 = (n + 15) / 16 * 16; s.pad_ = 0;
@@ -450,10 +459,11 @@ struct LockstepRun {
         S.flops += g.fl; S.flops_factor += g.flf; S.n_evals += g.nev;
         S.flops_chol += g.flf_chol; S.flops_trtri += g.flf_fit / 3; S.flops_lauum += g.flf_fit / 3;
         const bool roww = A >= OI_ROWWISE_MIN_SLOTS_HOST;
-        S.launches_chol += 2 * Nmax - 1 + (Nmax > 1 ? (roww ? Nmax - 1 : 1) : 0);
+        const int chol_l = (fused_chol && Nmax <= OI_MAX_NB) ? 1 : 2 * Nmax - 1;
+        S.launches_chol += chol_l + (Nmax > 1 ? (roww ? Nmax - 1 : 1) : 0);
         S.launches_trtri += std::max(0, Nmax - 1); S.launches_lauum += roww ? Nmax : 1;
         S.n_iterations++;
-        S.n_launches += (roww ? Nmax : 1) + (2 * Nmax - 1) + (Nmax > 1 ? (roww ? Nmax - 1 : 1) : 0) + 1 + std::max(0, Nmax - 1) + 1 +
+        S.n_launches += (roww ? Nmax : 1) + chol_l + (Nmax > 1 ? (roww ? Nmax - 1 : 1) : 0) + 1 + std::max(0, Nmax - 1) + 1 +
                         (roww ? Nmax : 1) + 1;
         size_t w = 0;
         const bool bulk = !is_express(gi) && n_express > 0 && A > express_cap;    // only big (slow) batches hand over
@@ -516,6 +526,7 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
         g.d_slots = h->d_slots + (size_t)gi * per; g.h_slots = h->h_slots + (size_t)gi * per;
         g.d_slot_phase = h->d_slot_phase + (size_t)gi * per; g.h_slot_phase = h->h_slot_phase + (size_t)gi * per;
         g.d_fail = h->d_fail + (size_t)gi * per;
+        g.d_ticket = h->d_tickets + gi * 32;
         g.slot_cap = per; g.active.clear(); g.in_flight = false;
     }
     R.pk = OiPacked{h->px, h->py, h->pt, h->pr};
@@ -532,6 +543,7 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
     if (const char* e = std::getenv("OI_EXPRESS_CAP")) R.express_cap = std::max(std::atoi(e), 1);
     R.iters.assign((size_t)nc, 0);
     R.graph_max_A = 32;
+    if (const char* e = std::getenv("OI_FUSED_CHOL")) R.fused_chol = std::atoi(e) != 0;
     if (const char* e = std::getenv("OI_GRAPH_MAX")) R.graph_max_A = std::max(std::atoi(e), 0);
     for (int gi = 0; gi < G; gi++) { OiGroup& g = *h->groups[gi]; g.gcells.clear(); g.last_cells.clear(); g.same_count = 0; }
     // work admitted per bulk group: enough tiles in flight to fill the GPU, few enough that an iteration stays short

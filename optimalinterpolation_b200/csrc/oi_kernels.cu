@@ -98,14 +98,7 @@ __global__ void __launch_bounds__(OI_THREADS) k_build(const OiSlot* __restrict__
     tile_build(s, ca, pk, i, j, ca.phase[s.cell] != OI_PH_PREDICT, smem);
 }
 
-#ifdef OI_EXP_ALIAS_DIAG
-#define OI_UPD_MINB 4
-#define OI_UPD_SMEM OI_SMEM_PIPE
-#else
-#define OI_UPD_MINB 3
-#define OI_UPD_SMEM OI_SMEM_BYTES
-#endif
-__global__ void __launch_bounds__(OI_THREADS, OI_UPD_MINB) k_chol_update(const OiSlot* __restrict__ slots, int k) {
+__global__ void __launch_bounds__(OI_THREADS, 3) k_chol_update(const OiSlot* __restrict__ slots, int k) {
     extern __shared__ __align__(16) double smem[];
     const OiSlot s = slots[blockIdx.y];
     const int i = k + blockIdx.x;
@@ -122,6 +115,63 @@ __global__ void __launch_bounds__(OI_THREADS, OI_PIPE_MINB) k_chol_panel(const O
     if (i >= s.N) return;
     if (OI_FAILED(s)) return;
     tile_chol_panel(s, i, k, smem);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// fused Cholesky: ONE launch for all block columns of all cells.  CTAs draw a ticket (atomic counter, so the
+// ticket order is the order in which CTAs start, whatever the hardware's dispatch order) and the tickets are laid
+// out column by column: [diagonal tiles of column k, all cells][off-diagonal tiles of column k, all cells] ...
+// A tile only ever waits for tiles with smaller tickets (which have started and never wait for larger ones), so
+// the chain always makes progress:
+//   tile (i,k), k > 0 : waits until the previous column of ITS cell is complete (col_done[k-1] == N-k)
+//   diagonal (k,k)    : update + factor + inverse, then publishes diag_done[k]
+//   off-diagonal (i,k): update, waits for diag_done[k], panel product L_ik = A_ik L_kk^-T, then col_done[k] += 1
+// There are no launch boundaries between the 2N dependent steps: a cell's next column starts as soon as that
+// cell is ready, the serial 64x64 factorisations hide behind the other cells' tiles, and small batches save the
+// launch gaps.  A failed factorisation still publishes its flags (the tiles behind it skip their work).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void wait_flag_ge(const int* p, int target) {     // thread 0 spins, the CTA follows
+    if (threadIdx.x == 0) {
+        while (ld_acquire_s32(p) < target) __nanosleep(64);
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(OI_THREADS, 3) k_chol_fused(const OiSlot* __restrict__ slots, OiCholPlan plan, int* __restrict__ ticket) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_t[4];
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(ticket, 1);
+        int seg = 0;
+        while (seg + 1 < 2 * plan.Nmax && plan.off[seg + 1] <= t) seg++;
+        const int k = seg >> 1, local = t - plan.off[seg];
+        int slot, i;
+        if ((seg & 1) == 0) { slot = local; i = k; }
+        else { const int tpc = plan.Nmax - k - 1; slot = local / tpc; i = k + 1 + local % tpc; }
+        s_t[0] = k; s_t[1] = slot; s_t[2] = i;
+    }
+    __syncthreads();
+    const int k = s_t[0], i = s_t[2];
+    const OiSlot s = slots[s_t[1]];
+    if (i >= s.N) return;
+    int* diag_done = s.flags;
+    int* col_done = s.flags + s.N;
+    if (k > 0) wait_flag_ge(&col_done[k - 1], s.N - k);          // all N-k off-diagonal tiles of column k-1 are final
+    if (!OI_FAILED(s)) tile_chol_update(s, i, k, smem);
+    __syncthreads();
+    if (i == k) {
+        if (threadIdx.x == 0) { __threadfence(); atomicExch(&diag_done[k], 1); }
+        return;
+    }
+    wait_flag_ge(&diag_done[k], 1);
+    if (!OI_FAILED(s)) tile_chol_panel(s, i, k, smem);
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); atomicAdd(&col_done[k], 1); }
 }
 
 __global__ void __launch_bounds__(256) k_fwd(const OiSlot* __restrict__ slots, OiCellArrays ca, OiPacked pk, double t_pred) {
@@ -251,7 +301,8 @@ __global__ void __launch_bounds__(OI_THREADS, 3) k_gp_persistent(OiPersist P, Oi
             s.Dinv = (double*)(scratch + off); off += ((size_t)N * OI_TILE * 8 + 255) & ~(size_t)255;
             s.vec = (double*)(scratch + off); off += ((size_t)3 * npad * 8 + 255) & ~(size_t)255;
             s.part = (double*)(scratch + off); off += ((size_t)(N + 8 + 5 * N * (N + 1) / 2) * 8 + 255) & ~(size_t)255;
-            s.QE = (double*)(scratch + off);
+            s.QE = (double*)(scratch + off); off += ((size_t)N * (N + 1) / 2 * 2 * OI_TILE * 8 + 255) & ~(size_t)255;
+            s.flags = (int*)(scratch + off);
             s.fail = P.fail + grp;
             s.pt_off = w.pt_off; s.cell = w.cell; s.n = w.n; s.npad = npad; s.N = N; s.n16 = (w.n + 15) / 16 * 16; s.pad_ = 0;
         }
@@ -334,6 +385,7 @@ static void set_attrs() {
     if (g_attr_done) return;
     cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_BYTES);
     cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_PIPE);
+    cudaFuncSetAttribute(k_chol_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_BYTES);
     cudaFuncSetAttribute(k_trtri, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_PIPE);
     cudaFuncSetAttribute(k_scale_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_BYTES);
     cudaFuncSetAttribute(k_lauum_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_PIPE);
@@ -372,12 +424,25 @@ void oi_launch_build(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, Oi
 }
 void oi_launch_chol_update(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int k, cudaStream_t st) {
     set_attrs();
-    k_chol_update<<<dim3(k == 0 ? 1 : Nmax - k, cnt_gt[k]), OI_THREADS, OI_UPD_SMEM, st>>>(slots, k);
+    k_chol_update<<<dim3(k == 0 ? 1 : Nmax - k, cnt_gt[k]), OI_THREADS, OI_SMEM_BYTES, st>>>(slots, k);
 }
 void oi_launch_chol_panel(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int k, cudaStream_t st) {
     set_attrs();
     if (Nmax - k - 1 <= 0 || cnt_gt[k + 1] <= 0) return;
     k_chol_panel<<<dim3(Nmax - k - 1, cnt_gt[k + 1]), OI_THREADS, OI_SMEM_PIPE, st>>>(slots, k);
+}
+// all block columns in one launch; ticket must be zero (the caller resets it on the stream before the launch)
+void oi_launch_chol_fused(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int* ticket, cudaStream_t st) {
+    set_attrs();
+    OiCholPlan plan;
+    plan.Nmax = Nmax;
+    int off = 0;
+    for (int k = 0; k < Nmax; k++) {
+        plan.off[2 * k] = off; off += cnt_gt[k];                              // diagonal tiles: cells with N > k
+        plan.off[2 * k + 1] = off; off += cnt_gt[k + 1] * (Nmax - k - 1);     // off-diagonal: cells with N > k+1
+    }
+    plan.off[2 * Nmax] = off;
+    if (off > 0) k_chol_fused<<<off, OI_THREADS, OI_SMEM_BYTES, st>>>(slots, plan, ticket);
 }
 void oi_launch_fwd(const OiSlot* slots, int A, OiCellArrays ca, OiPacked pk, double t_pred, cudaStream_t st) {
     k_fwd<<<A, 256, SMALL_SMEM, st>>>(slots, ca, pk, t_pred);

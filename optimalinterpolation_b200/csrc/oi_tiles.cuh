@@ -81,7 +81,10 @@ __device__ __forceinline__ double pair_Q(double dx, double dy, double dt) {
 __device__ __forceinline__ void tile_build(const OiSlot& s, const OiCellArrays& ca, const OiPacked& pk, int i, int j, bool want_qe,
                                            double* smem) {
     const int tid = threadIdx.x;
-    if (i == 0 && tid == 0) *s.fail = 0;
+    if (i == 0) {
+        if (tid == 0) *s.fail = 0;
+        for (int q = tid; q < 2 * s.N; q += OI_THREADS) s.flags[q] = 0;      // dependency flags of k_chol_fused
+    }
     double(*ru)[NB] = (double(*)[NB])smem;
     double(*cu)[NB] = ru + 3;
     const double* h = ca.hyp + 5 * (size_t)s.cell;
@@ -245,6 +248,7 @@ __device__ __forceinline__ void diag_factor_invert(double* T, double* W, double*
 #pragma unroll
             for (int c = 0; c < 8; c++) a[c] = T[(jb + r) * TS + jb + c];
             bool bad = false;
+            double dinv[8];                                                  // 1 / L[c][c], known to every lane
 #pragma unroll
             for (int c = 0; c < 8; c++) {
 #pragma unroll
@@ -255,6 +259,7 @@ __device__ __forceinline__ void diag_factor_invert(double* T, double* W, double*
                 double piv = __shfl_sync(0xffffffffu, a[c], c, 8);
                 if (piv <= 0.0) bad = true;
                 double sq = sqrt(piv), inv = 1.0 / sq;
+                dinv[c] = inv;
                 if (r == c) a[c] = sq;
                 else if (r > c) a[c] *= inv;
             }
@@ -274,8 +279,7 @@ __device__ __forceinline__ void diag_factor_invert(double* T, double* W, double*
                     double sacc = 0.0;
 #pragma unroll
                     for (int l = 0; l < rr; l++) sacc = fma(T[(jb + rr) * TS + jb + l], x[l], sacc);
-                    double dinv = 1.0 / T[(jb + rr) * TS + jb + rr];
-                    x[rr] = (rr < b) ? 0.0 : ((rr == b) ? dinv : -sacc * dinv);
+                    x[rr] = (rr < b) ? 0.0 : ((rr == b) ? dinv[rr] : -sacc * dinv[rr]);
                 }
                 if (lane < 8) {
 #pragma unroll
@@ -284,9 +288,7 @@ __device__ __forceinline__ void diag_factor_invert(double* T, double* W, double*
             }
         }
         __syncthreads();
-#ifndef OI_EXP_ALIAS_DIAG
         if (*s_bad) return;
-#endif
         // panel: L_ij = A_ij * X_jj^T  (i > j)
         for (int i = j + 1 + warp; i < 8; i += 4) {
             double c2[2] = {0.0, 0.0};
@@ -384,16 +386,9 @@ __device__ __forceinline__ void tile_chol_update(const OiSlot& s, int i, int k, 
     }
     // ---- diagonal tile: T = A_kk - acc, factor + invert in shared memory ----
     double* T = smem;                    // [64][TS]  A_kk -> L_kk (lower)
-#ifdef OI_EXP_ALIAS_DIAG
-    // TIMING EXPERIMENT ONLY (wrong numbers): W aliases T so that the CTA needs 37 KB instead of 72 KB
-    double* W = smem;
-    double* sc = smem + NB * TS + warp * 64;
-    int* s_bad = (int*)(smem + NB * TS + 4 * 64);
-#else
     double* W = smem + NB * TS;          // [64][TS]  L_kk^-1 (lower, zeros above)
     double* sc = smem + 2 * NB * TS + warp * 64;   // per-warp 8x8 scratch
     int* s_bad = (int*)(smem + 2 * NB * TS + 4 * 64);
-#endif
 #pragma unroll
     for (int mb = 0; mb < 4; mb++)
 #pragma unroll
@@ -406,12 +401,10 @@ __device__ __forceinline__ void tile_chol_update(const OiSlot& s, int i, int k, 
     if (tid == 0) *s_bad = 0;
     __syncthreads();
     diag_factor_invert(T, W, sc, s_bad, tid);
-#ifndef OI_EXP_ALIAS_DIAG
     if (*s_bad) {
         if (tid == 0) *s.fail = 1;
         return;
     }
-#endif
     if (warp == 0) {
         // log-determinant part: sum_i log L_ii of this block (GPR_CS2S3.py:128), fixed order
         double v = log(T[lane * TS + lane]) + log(T[(lane + 32) * TS + lane + 32]);

@@ -18,6 +18,7 @@ struct OiSlot {
     double* QE;       // per lower tile (i,j): 64x64 Q = scaled distances, then 64x64 E = exp(-Q), written by the covariance
                       // build and re-read by the trace epilogue (trades FP64-pipe work, shared with DMMA, for idle HBM bandwidth)
     int* fail;        // set when a Cholesky pivot is <= 0 or NaN (np.linalg.LinAlgError in the reference)
+    int* flags;       // [2N] dependency flags of the fused Cholesky: diag_done[k] | col_done[k] (finished off-diagonal tiles)
     long long pt_off; // offset of this cell's points in the packed (CSR-ordered) coordinate arrays
     int cell, n, npad, N;
     int n16, pad_;    // n rounded up to the DMMA K chunk (16): K loops and edge sub-tiles stop here
@@ -57,3 +58,8 @@ struct OiPersist {
     int evals_cap;                     // evaluations a group spends on one cell before it takes the next
     OiPersistAcc* acc;
 };
+
+// ---- fused Cholesky (oi_kernels.cu: k_chol_fused): CTA tickets are laid out column by column,
+// segment 2k = diagonal tiles (k,k) of all cells with N > k, segment 2k+1 = off-diagonal tiles of column k
+#define OI_MAX_NB 128
+struct OiCholPlan { int Nmax; int off[2 * OI_MAX_NB + 1]; };

@@ -192,10 +192,12 @@ def test_engines_and_groupings_bit_identical(small_day):
     import os
     ref = None
     for kw in (dict(engine=0, n_groups=1), dict(engine=0, n_groups=8), dict(engine=0, n_groups=3, max_active=7),
-               dict(engine=0, n_groups=4, express=(2, 5, 3)), dict(engine=0, n_groups=2, nograph=True),
+               dict(engine=0, n_groups=4, express=(2, 5, 3)), dict(engine=0, n_groups=2, nograph=True), dict(engine=0, n_groups=2, unfused=True),
                dict(engine=1, group_size=1), dict(engine=1, group_size=3, evals_per_launch=5), dict(engine=1, group_size=8)):
         kw = dict(kw)
         ex = kw.pop("express", None)
+        if kw.pop("unfused", False):     # two launches per block column instead of the single-launch fused Cholesky
+            os.environ["OI_FUSED_CHOL"] = "0"
         if kw.pop("nograph", False):     # the first configurations replay CUDA graphs (batches <= 32 cells); this one does not
             os.environ["OI_GRAPH_MAX"] = "0"
         if ex:   # force the express-lane hand-over (lanes, after-iterations, lane capacity) on this tiny problem
@@ -203,7 +205,7 @@ def test_engines_and_groupings_bit_identical(small_day):
         try:
             h.run(h.make_params(d.radius_km * 1000.0, d.T_mid, d.mean, d.x0, mode=0, **kw))
         finally:
-            for k in ("OI_EXPRESS", "OI_EXPRESS_AFTER", "OI_EXPRESS_CAP", "OI_GRAPH_MAX"):
+            for k in ("OI_EXPRESS", "OI_EXPRESS_AFTER", "OI_EXPRESS_CAP", "OI_GRAPH_MAX", "OI_FUSED_CHOL"):
                 os.environ.pop(k, None)
         if ex:
             assert h.stats()["n_express_cells"] > 0

@@ -14,7 +14,12 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 d = make_day()
 cells = np.arange(0, len(d.X), stride)
 h = oi.Handle(0)
-h.set_observations(d.x_train, d.y_train, d.t_train, d.z); h.set_cells(d.X[cells]); h.gather_neighbours(d.radius_km * 1000.0)
+h.set_observations(d.x_train, d.y_train, d.t_train, d.z); h.set_cells(d.X[cells]); cnt = h.gather_neighbours(d.radius_km * 1000.0)
+if os.environ.get("OI_NRANGE"):          # OI_NRANGE=lo,hi: only cells with lo <= n <= hi
+    lo, hi = map(int, os.environ["OI_NRANGE"].split(","))
+    cells = cells[(cnt >= lo) & (cnt <= hi)]
+    h.set_cells(d.X[cells]); cnt = h.gather_neighbours(d.radius_km * 1000.0)
+    print("n range", lo, hi, "->", len(cells), "cells, mean n", cnt.mean())
 hyp = np.log([2.15e5, 1.40e5, 21.0, 0.0279, 0.00346, 0.1])
 walls = []
 for r in range(reps):
