@@ -308,14 +308,18 @@ struct LockstepRun {
     long long cell_tiles(int c) const { long long N = (h->h_counts[c] + OI_NB - 1) / OI_NB; return N * (N + 1) / 2; }
 
     int graph_max_A = 0;            // batches up to this many cells replay a captured graph
-    bool fused_chol = false;        // OI_FUSED_CHOL=1: one launch for all block columns (k_chol_fused); measured slower, off
+    // k_chol_fused (one launch for all block columns): 0 never, 1 always, 2 only for small batches (<= graph_max_A cells)
+    int fused_chol = 0;
+    bool use_fused(int A, int Nmax) const {
+        return Nmax <= OI_MAX_NB && (fused_chol == 1 || (fused_chol == 2 && A <= graph_max_A));
+    }
 
     // the kernel chain of one lockstep iteration of group g (timed: with the family boundary events)
     int launch_chain(OiGroup& g, int A, int Nmax, const int* cg, cudaStream_t st, bool timed) {
         if (timed) CK(cudaEventRecord(g.ev[0], st));
         oi_launch_build(g.d_slots, A, Nmax, cg, h->ca, pk, st);
         if (timed) CK(cudaEventRecord(g.ev[1], st));
-        if (fused_chol && Nmax <= OI_MAX_NB) {
+        if (use_fused(A, Nmax)) {
             CK(cudaMemsetAsync(g.d_ticket, 0, 4, st));
             oi_launch_chol_fused(g.d_slots, A, Nmax, cg, g.d_ticket, st);
         } else {
@@ -459,7 +463,7 @@ struct LockstepRun {
         S.flops += g.fl; S.flops_factor += g.flf; S.n_evals += g.nev;
         S.flops_chol += g.flf_chol; S.flops_trtri += g.flf_fit / 3; S.flops_lauum += g.flf_fit / 3;
         const bool roww = A >= OI_ROWWISE_MIN_SLOTS_HOST;
-        const int chol_l = (fused_chol && Nmax <= OI_MAX_NB) ? 1 : 2 * Nmax - 1;
+        const int chol_l = use_fused(A, Nmax) ? 1 : 2 * Nmax - 1;
         S.launches_chol += chol_l + (Nmax > 1 ? (roww ? Nmax - 1 : 1) : 0);
         S.launches_trtri += std::max(0, Nmax - 1); S.launches_lauum += roww ? Nmax : 1;
         S.n_iterations++;
@@ -543,7 +547,7 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
     if (const char* e = std::getenv("OI_EXPRESS_CAP")) R.express_cap = std::max(std::atoi(e), 1);
     R.iters.assign((size_t)nc, 0);
     R.graph_max_A = 32;
-    if (const char* e = std::getenv("OI_FUSED_CHOL")) R.fused_chol = std::atoi(e) != 0;
+    if (const char* e = std::getenv("OI_FUSED_CHOL")) R.fused_chol = std::atoi(e);
     if (const char* e = std::getenv("OI_GRAPH_MAX")) R.graph_max_A = std::max(std::atoi(e), 0);
     for (int gi = 0; gi < G; gi++) { OiGroup& g = *h->groups[gi]; g.gcells.clear(); g.last_cells.clear(); g.same_count = 0; }
     // work admitted per bulk group: enough tiles in flight to fill the GPU, few enough that an iteration stays short

@@ -192,12 +192,12 @@ def test_engines_and_groupings_bit_identical(small_day):
     import os
     ref = None
     for kw in (dict(engine=0, n_groups=1), dict(engine=0, n_groups=8), dict(engine=0, n_groups=3, max_active=7),
-               dict(engine=0, n_groups=4, express=(2, 5, 3)), dict(engine=0, n_groups=2, nograph=True), dict(engine=0, n_groups=2, unfused=True),
+               dict(engine=0, n_groups=4, express=(2, 5, 3)), dict(engine=0, n_groups=2, nograph=True), dict(engine=0, n_groups=2, fused=True),
                dict(engine=1, group_size=1), dict(engine=1, group_size=3, evals_per_launch=5), dict(engine=1, group_size=8)):
         kw = dict(kw)
         ex = kw.pop("express", None)
-        if kw.pop("unfused", False):     # two launches per block column instead of the single-launch fused Cholesky
-            os.environ["OI_FUSED_CHOL"] = "0"
+        if kw.pop("fused", False):       # single-launch fused Cholesky (ticketed dependency flags) instead of 2 launches per column
+            os.environ["OI_FUSED_CHOL"] = "1"
         if kw.pop("nograph", False):     # the first configurations replay CUDA graphs (batches <= 32 cells); this one does not
             os.environ["OI_GRAPH_MAX"] = "0"
         if ex:   # force the express-lane hand-over (lanes, after-iterations, lane capacity) on this tiny problem
