@@ -84,6 +84,9 @@ extern "C" const char* oi_last_error(void) { return g_err.c_str(); }
 
 extern "C" int oi_create(int device, oi_handle** out) {
     if (!out) return fail(OI_ERR_ARG, "oi_create: out is NULL");
+    // The stream groups need their own hardware queues: with the default of 8 connections, streams alias and
+    // serialise (measured +2 % with 32).  Only effective if the CUDA context does not exist yet; never overrides the user.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)

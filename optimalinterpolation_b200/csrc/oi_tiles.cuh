@@ -238,57 +238,76 @@ __device__ __forceinline__ void gemm_nt_stream(double (&acc)[4][4][2], const dou
 // semantics, which is what np.linalg.cholesky runs), every other sub-block operation (panel solve,
 // trailing update, inverse by block distance) is one or two DMMA m8n8k4 per 8x8 block.
 // ------------------------------------------------------------------------------------------
+// 8x8 pivot block (jb, jb) of T: Cholesky factor in place (lower) and its inverse into W, by one warp in registers
+// (lane r = row r; the four groups of 8 lanes do the same work).  dpotf2 order of operations.
+__device__ __forceinline__ void pivot_factor_invert(double* T, double* W, int jb, int lane, int* s_bad) {
+    const int r = lane & 7;
+    double a[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) a[c] = T[(jb + r) * TS + jb + c];
+    bool bad = false;
+    double dinv[8];                                                  // 1 / L[c][c], known to every lane
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+#pragma unroll
+        for (int l = 0; l < c; l++) {
+            double acl = __shfl_sync(0xffffffffu, a[l], c, 8);      // L[c][l]
+            if (r >= c) a[c] = fma(-a[l], acl, a[c]);
+        }
+        double piv = __shfl_sync(0xffffffffu, a[c], c, 8);
+        if (piv <= 0.0) bad = true;
+        double sq = sqrt(piv), inv = 1.0 / sq;
+        dinv[c] = inv;
+        if (r == c) a[c] = sq;
+        else if (r > c) a[c] *= inv;
+    }
+    if (bad) {
+        if (lane == 0) *s_bad = 1;
+        return;
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) if (c <= r) T[(jb + r) * TS + jb + c] = a[c];
+    }
+    __syncwarp();
+    // X = L8^-1, lane b owns column b:  x[rr] = -(sum_{l<rr} L[rr][l] x[l]) / L[rr][rr]
+    const int b = r;
+    double x[8];
+#pragma unroll
+    for (int rr = 0; rr < 8; rr++) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int l = 0; l < rr; l++) sacc = fma(T[(jb + rr) * TS + jb + l], x[l], sacc);
+        x[rr] = (rr < b) ? 0.0 : ((rr == b) ? dinv[rr] : -sacc * dinv[rr]);
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int rr = 0; rr < 8; rr++) if (rr >= b) W[(jb + rr) * TS + jb + b] = x[rr];
+    }
+}
+
+// trailing update of one 8x8 block of the diagonal tile: A_il -= L_ij L_lj^T
+__device__ __forceinline__ void diag_trailing_block(double* T, int i, int l, int jb, int fr, int fc) {
+    double c2[2];
+    c2[0] = T[(i * 8 + fr) * TS + l * 8 + fc * 2];
+    c2[1] = T[(i * 8 + fr) * TS + l * 8 + fc * 2 + 1];
+#pragma unroll
+    for (int ks = 0; ks < 2; ks++)
+        dmma(c2, -T[(i * 8 + fr) * TS + jb + ks * 4 + fc], T[(l * 8 + fr) * TS + jb + ks * 4 + fc]);
+    T[(i * 8 + fr) * TS + l * 8 + fc * 2] = c2[0];
+    T[(i * 8 + fr) * TS + l * 8 + fc * 2 + 1] = c2[1];
+}
+
+// The 64 pivots are one dependent chain run by warp 0 (the critical path of the kernel's diagonal CTAs), so the
+// chain is overlapped with the DMMA work: after the panel of step j, warp 0 updates only the next pivot block and
+// factors it (look-ahead) while warps 1-3 apply the rest of step j's trailing update.
 __device__ __forceinline__ void diag_factor_invert(double* T, double* W, double* sc, int* s_bad, int tid) {
     const int warp = tid >> 5, lane = tid & 31, fr = lane >> 2, fc = lane & 3;
+    if (warp == 0) pivot_factor_invert(T, W, 0, lane, s_bad);
+    __syncthreads();
+    if (*s_bad) return;
     for (int j = 0; j < 8; j++) {
         const int jb = j * 8;
-        if (warp == 0) {
-            const int r = lane & 7;
-            double a[8];
-#pragma unroll
-            for (int c = 0; c < 8; c++) a[c] = T[(jb + r) * TS + jb + c];
-            bool bad = false;
-            double dinv[8];                                                  // 1 / L[c][c], known to every lane
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-#pragma unroll
-                for (int l = 0; l < c; l++) {
-                    double acl = __shfl_sync(0xffffffffu, a[l], c, 8);      // L[c][l]
-                    if (r >= c) a[c] = fma(-a[l], acl, a[c]);
-                }
-                double piv = __shfl_sync(0xffffffffu, a[c], c, 8);
-                if (piv <= 0.0) bad = true;
-                double sq = sqrt(piv), inv = 1.0 / sq;
-                dinv[c] = inv;
-                if (r == c) a[c] = sq;
-                else if (r > c) a[c] *= inv;
-            }
-            if (bad) {
-                if (lane == 0) *s_bad = 1;
-            } else {
-                if (lane < 8) {
-#pragma unroll
-                    for (int c = 0; c < 8; c++) if (c <= r) T[(jb + r) * TS + jb + c] = a[c];
-                }
-                __syncwarp();
-                // X = L8^-1, lane b owns column b:  x[rr] = -(sum_{l<rr} L[rr][l] x[l]) / L[rr][rr]
-                const int b = r;
-                double x[8];
-#pragma unroll
-                for (int rr = 0; rr < 8; rr++) {
-                    double sacc = 0.0;
-#pragma unroll
-                    for (int l = 0; l < rr; l++) sacc = fma(T[(jb + rr) * TS + jb + l], x[l], sacc);
-                    x[rr] = (rr < b) ? 0.0 : ((rr == b) ? dinv[rr] : -sacc * dinv[rr]);
-                }
-                if (lane < 8) {
-#pragma unroll
-                    for (int rr = 0; rr < 8; rr++) if (rr >= b) W[(jb + rr) * TS + jb + b] = x[rr];
-                }
-            }
-        }
-        __syncthreads();
-        if (*s_bad) return;
         // panel: L_ij = A_ij * X_jj^T  (i > j)
         for (int i = j + 1 + warp; i < 8; i += 4) {
             double c2[2] = {0.0, 0.0};
@@ -300,22 +319,23 @@ __device__ __forceinline__ void diag_factor_invert(double* T, double* W, double*
             T[(i * 8 + fr) * TS + jb + fc * 2 + 1] = c2[1];
         }
         __syncthreads();
-        // trailing update: A_il -= L_ij L_lj^T  (j < l <= i)
+        if (j == 7) break;
+        // trailing update: A_il -= L_ij L_lj^T  (j < l <= i); block q = 0 is the next pivot block (j+1, j+1)
         const int m = 7 - j, cnt = m * (m + 1) / 2;
-        for (int q = warp; q < cnt; q += 4) {
-            int ii, ll;
-            tile_ij(q, ii, ll);
-            const int i = j + 1 + ii, l = j + 1 + ll;
-            double c2[2];
-            c2[0] = T[(i * 8 + fr) * TS + l * 8 + fc * 2];
-            c2[1] = T[(i * 8 + fr) * TS + l * 8 + fc * 2 + 1];
-#pragma unroll
-            for (int ks = 0; ks < 2; ks++)
-                dmma(c2, -T[(i * 8 + fr) * TS + jb + ks * 4 + fc], T[(l * 8 + fr) * TS + jb + ks * 4 + fc]);
-            T[(i * 8 + fr) * TS + l * 8 + fc * 2] = c2[0];
-            T[(i * 8 + fr) * TS + l * 8 + fc * 2 + 1] = c2[1];
+        if (warp == 0) {
+            diag_trailing_block(T, j + 1, j + 1, jb, fr, fc);
+            __syncwarp();
+            pivot_factor_invert(T, W, jb + 8, lane, s_bad);
+        } else {
+            for (int q = warp; q < cnt; q += 3) {
+                int ii = 0;                                   // q -> (ii, ll), ll <= ii, integer only (cnt <= 28)
+                while ((ii + 1) * (ii + 2) / 2 <= q) ii++;
+                const int ll = q - ii * (ii + 1) / 2;
+                diag_trailing_block(T, j + 1 + ii, j + 1 + ll, jb, fr, fc);
+            }
         }
         __syncthreads();
+        if (*s_bad) return;
     }
     // inverse by 8x8 block distance: W_ik = -X_ii * sum_{j=k}^{i-1} L_ij W_jk
     for (int d = 1; d < 8; d++) {
