@@ -325,13 +325,13 @@ struct LockstepRun {
         if (use_fused(A, Nmax)) {
             CK(cudaMemsetAsync(g.d_ticket, 0, 4, st));
             oi_launch_chol_fused(g.d_slots, A, Nmax, cg, g.d_ticket, st);
+            oi_launch_scale_rows(g.d_slots, A, Nmax, cg, st);
         } else {
             for (int k = 0; k < Nmax; k++) {
                 oi_launch_chol_update(g.d_slots, A, Nmax, cg, k, st);
-                oi_launch_chol_panel(g.d_slots, A, Nmax, cg, k, st);
+                oi_launch_chol_panel(g.d_slots, A, Nmax, cg, k, st);      // panel of column k + row scaling of row k
             }
         }
-        oi_launch_scale_rows(g.d_slots, A, Nmax, cg, st);
         if (timed) CK(cudaEventRecord(g.ev[2], st));
         oi_launch_fwd(g.d_slots, A, h->ca, pk, t_pred, st);
         if (timed) CK(cudaEventRecord(g.ev[3], st));
@@ -467,10 +467,11 @@ struct LockstepRun {
         S.flops_chol += g.flf_chol; S.flops_trtri += g.flf_fit / 3; S.flops_lauum += g.flf_fit / 3;
         const bool roww = A >= OI_ROWWISE_MIN_SLOTS_HOST;
         const int chol_l = use_fused(A, Nmax) ? 1 : 2 * Nmax - 1;
-        S.launches_chol += chol_l + (Nmax > 1 ? (roww ? Nmax - 1 : 1) : 0);
+        const int scale_l = use_fused(A, Nmax) ? (Nmax > 1 ? (roww ? Nmax - 1 : 1) : 0) : (Nmax > 1 ? 1 : 0);   // unfused: 2N launches in all
+        S.launches_chol += chol_l + scale_l;
         S.launches_trtri += std::max(0, Nmax - 1); S.launches_lauum += roww ? Nmax : 1;
         S.n_iterations++;
-        S.n_launches += (roww ? Nmax : 1) + chol_l + (Nmax > 1 ? (roww ? Nmax - 1 : 1) : 0) + 1 + std::max(0, Nmax - 1) + 1 +
+        S.n_launches += (roww ? Nmax : 1) + chol_l + scale_l + 1 + std::max(0, Nmax - 1) + 1 +
                         (roww ? Nmax : 1) + 1;
         size_t w = 0;
         const bool bulk = !is_express(gi) && n_express > 0 && A > express_cap;    // only big (slow) batches hand over

@@ -108,13 +108,20 @@ __global__ void __launch_bounds__(OI_THREADS, 3) k_chol_update(const OiSlot* __r
     tile_chol_update(s, i, k, smem);
 }
 
-__global__ void __launch_bounds__(OI_THREADS, OI_PIPE_MINB) k_chol_panel(const OiSlot* __restrict__ slots, int k) {
+// Everything that only waits for Dinv[k]: the panel tiles (i, k), i > k, and -- row k of L being final once block
+// column k has been updated -- the row scaling Ls_kj = L_kk^-1 L_kj of row k (j < k).  One launch, no extra pass.
+__global__ void __launch_bounds__(OI_THREADS, 3) k_chol_panel(const OiSlot* __restrict__ slots, int k, int n_panel) {
     extern __shared__ __align__(16) double smem[];
     const OiSlot s = slots[blockIdx.y];
-    const int i = k + 1 + blockIdx.x;
-    if (i >= s.N) return;
+    if (k >= s.N) return;
     if (OI_FAILED(s)) return;
-    tile_chol_panel(s, i, k, smem);
+    if ((int)blockIdx.x < n_panel) {
+        const int i = k + 1 + blockIdx.x;
+        if (i < s.N) tile_chol_panel(s, i, k, smem);
+    } else {
+        const int j = blockIdx.x - n_panel;
+        if (j < k) tile_scale(s, k, j, smem);
+    }
 }
 
 
@@ -384,7 +391,7 @@ static bool g_attr_done = false;
 static void set_attrs() {
     if (g_attr_done) return;
     cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_BYTES);
-    cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_PIPE);
+    cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_BYTES);
     cudaFuncSetAttribute(k_chol_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_BYTES);
     cudaFuncSetAttribute(k_trtri, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_PIPE);
     cudaFuncSetAttribute(k_scale_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_BYTES);
@@ -428,8 +435,9 @@ void oi_launch_chol_update(const OiSlot* slots, int A, int Nmax, const int* cnt_
 }
 void oi_launch_chol_panel(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int k, cudaStream_t st) {
     set_attrs();
-    if (Nmax - k - 1 <= 0 || cnt_gt[k + 1] <= 0) return;
-    k_chol_panel<<<dim3(Nmax - k - 1, cnt_gt[k + 1]), OI_THREADS, OI_SMEM_PIPE, st>>>(slots, k);
+    const int n_panel = cnt_gt[k + 1] > 0 ? Nmax - k - 1 : 0;     // panel tiles exist for cells with N > k+1, row k for N > k
+    if (n_panel + k <= 0 || cnt_gt[k] <= 0) return;
+    k_chol_panel<<<dim3(n_panel + k, cnt_gt[k]), OI_THREADS, OI_SMEM_BYTES, st>>>(slots, k, n_panel);
 }
 // all block columns in one launch; ticket must be zero (the caller resets it on the stream before the launch)
 void oi_launch_chol_fused(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int* ticket, cudaStream_t st) {
