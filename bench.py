@@ -97,17 +97,20 @@ def reference_arm(args, rank, world):
     counts = np.asarray(cKDTree(np.c_[day.x_train, day.y_train]).query_ball_point(
         day.X, r=day.radius_km * 1000.0, return_length=True))
     cores = os.cpu_count() or 1
+    # evaluations per cell: full scipy-CG fits of the cheapest cells (nfev hardly depends on n: 158 +- 40 over n = 169..1100
+    # in tests/golden/day_fit_sample_large.npz), untimed
+    rf = cpu_baseline.run_sample(day, counts, cells, cores=cores, frac=0.02)
+    nfev_mean = rf["nfev_mean"]
     vals, wall = [], []
     for s in range(args.warmup + args.steps):
-        # warm-up steps use a much cheaper sample (processes/BLAS spin-up only)
-        frac = 0.02 if s < args.warmup else args.cpu_frac * 0.5
-        r = cpu_baseline.run_sample(day, counts, cells, cores=cores, frac=frac)
+        r = cpu_baseline.run_eval_sample(day, counts, cells, nfev=nfev_mean, cores=cores)
         if s >= args.warmup:
             vals.append(r["value"]); wall.append(r["wall_s"]); last = r
     v = float(np.mean(vals))
-    sample = (f"{last['n_sample']} cells per step evenly from the cheapest {args.cpu_frac * 0.5:.0%} of the step's "
-              f"{len(cells)} cells (n {last['n_min']}..{last['n_max']}), one process per core, 1 BLAS thread each; "
-              f"cells/s scaled by the n^3 cost ratio {last['cost_ratio']:.4f} to the step's cost mix")
+    sample = (f"per step one SMLII evaluation timed on {last['n_sample']} cells at evenly spaced quantiles of the step's n-distribution "
+              f"(n {last['n_min']}..{last['n_max']}), one process per core, 1 BLAS thread each; t(n) ~ n^{last['exponent']:.2f}; cost of the "
+              f"step = sum over its {len(cells)} cells of (nfev + 1/3) * t(n), nfev {nfev_mean:.0f} = mean of full scipy-CG fits of the "
+              f"{rf['n_sample']} cheapest cells; {last['core_hours']:.1f} core-hours for the step")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "cells/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(wall)) * 1e3,
@@ -308,14 +311,16 @@ def main():
             warnings.simplefilter("ignore")
             from oracle import cpu_baseline
             cores = os.cpu_count() or 1
-            cpu_baseline.run_sample(day, counts_full(day, h, cells, counts_step), cells, cores=cores, frac=0.02)
-            r = cpu_baseline.run_sample(day, counts_full(day, h, cells, counts_step), cells, cores=cores, frac=args.cpu_frac)
+            cf = counts_full(day, h, cells, counts_step)
+            nf = np.zeros(len(cells)); nf[mine] = res["nfev"]            # evaluations per cell as measured in the GPU run
+            r = cpu_baseline.run_eval_sample(day, cf, cells, nfev=nf, cores=cores)
             line["cpu_baseline"] = {
                 "value": r["value"], "unit": "cells/s", "cores": cores, "kind": "port",
-                "sample": (f"{r['n_sample']} cells evenly from the cheapest {args.cpu_frac:.0%} of the step's {len(cells)} cells "
-                           f"(n {r['n_min']}..{r['n_max']}), full scipy-CG fit + predict each, one process per core with 1 BLAS "
-                           f"thread, {r['wall_s']:.1f} s wall; raw {r['raw_cells_per_s']:.4f} cells/s scaled by the n^3 cost "
-                           f"ratio {r['cost_ratio']:.4f} to the step's cost mix")}
+                "sample": (f"one SMLII evaluation (the reference spends >99% of its time there) timed on {r['n_sample']} cells at evenly "
+                           f"spaced quantiles of the step's n-distribution (n {r['n_min']}..{r['n_max']}), one process per core with 1 BLAS "
+                           f"thread, {r['wall_s']:.1f} s wall; power-law fit t(n) ~ n^{r['exponent']:.2f} ({r['t_eval_median_n'] * 1e3:.0f} ms at the "
+                           f"median n); cost of the step = sum over its {len(cells)} cells of (nfev + 1/3) * t(n) with the measured mean "
+                           f"nfev {r['nfev_mean']:.0f} = {r['core_hours']:.1f} core-hours")}
         print(json.dumps(line))
     h.close()
     if world > 1:
