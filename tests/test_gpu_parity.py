@@ -264,3 +264,32 @@ def test_ragged_block_edges_and_empty_cells():
         got = res["out"][k]
         assert abs(got[0] - fs) <= 1e-9 * abs(fs) and abs(got[1] - sfs2) <= 1e-9 * abs(sfs2) and abs(got[2] - lZ) <= 1e-9 * max(abs(lZ), 1.0), (n, got[:3], (fs, sfs2, lZ))
     h.close()
+
+
+def test_first_cg_iterations_match_scipy(small_day, small_oracle):
+    """Before round-off differences can steer a line search elsewhere, the device optimiser must walk scipy's path:
+    with maxiter = 3 (scipy options={'maxiter': 3}) the number of evaluations and the warn flag are equal and the
+    hyperparameters agree to 1e-7; same with a loose gtol that stops some cells early with status 0."""
+    import warnings
+    import scipy.optimize
+    import optimalinterpolation_b200 as oi
+    from oracle.gpr_oracle import nlml_grad
+    d, o = small_day, small_oracle
+    cells = np.arange(3, len(d.X), 61)
+    h = oi.Handle(0)
+    h.set_observations(d.x_train, d.y_train, d.t_train, d.z); h.set_cells(d.X[cells]); h.gather_neighbours(d.radius_km * 1000.0)
+    for opts, kw in (({"maxiter": 3}, dict(maxiter=3)), ({"maxiter": 6, "gtol": 5.0}, dict(maxiter=6, gtol=5.0))):
+        h.run(h.make_params(d.radius_km * 1000.0, d.T_mid, d.mean, d.x0, mode=0, **kw))
+        res = h.get_results()
+        statuses = set()
+        for k, c in enumerate(cells):
+            _, inp, out, _ = o.cell_data(int(c), sort=True)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                r = scipy.optimize.minimize(nlml_grad, list(d.x0), args=(inp, out, np.ones(len(out)) * d.mean), method="CG",
+                                            jac=True, options=opts)
+            assert res["nfev"][k] == r.nfev and res["status"][k] == r.status, (c, opts, res["nfev"][k], r.nfev, res["status"][k], r.status)
+            assert np.allclose(res["out"][k, 3:8], np.exp(r.x[:5]), rtol=1e-7, atol=0), (c, opts)
+            statuses.add(int(r.status))
+        print(opts, "statuses seen", statuses, "nfev", res["nfev"].tolist())
+    h.close()
