@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(OI_THREADS) k_build(const OiSlot* __restrict__
     tile_build(s, ca, pk, i, j, ca.phase[s.cell] != OI_PH_PREDICT, smem);
 }
 
-__global__ void __launch_bounds__(OI_THREADS, 3) k_chol_update(const OiSlot* __restrict__ slots, int k) {
+__global__ void __launch_bounds__(OI_THREADS, OI_PIPE_MINB) k_chol_update(const OiSlot* __restrict__ slots, int k) {
     extern __shared__ __align__(16) double smem[];
     const OiSlot s = slots[blockIdx.y];
     const int i = k + blockIdx.x;
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(OI_THREADS, 3) k_gp_persistent(OiPersist P, Oi
 static bool g_attr_done = false;
 static void set_attrs() {
     if (g_attr_done) return;
-    cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_BYTES);
+    cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_PIPE);
     cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_BYTES);
     cudaFuncSetAttribute(k_chol_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_BYTES);
     cudaFuncSetAttribute(k_trtri, cudaFuncAttributeMaxDynamicSharedMemorySize, OI_SMEM_PIPE);
@@ -401,6 +401,7 @@ static void set_attrs() {
 }
 static_assert(OI_SMEM_PIPE == PIPE_BYTES, "pipeline size");
 static_assert(OI_SMEM_BYTES >= PIPE_BYTES && OI_SMEM_BYTES >= 2 * NB * TS * 8 + 4 * 64 * 8 + 16, "shared memory budget");
+static_assert(PIPE_BYTES >= NB * TS * 8 + 4 * 64 * 8 + 16, "packed diagonal block must fit the pipeline buffers");
 
 void oi_launch_count(const double* ox, const double* oy, int n_obs, const double* X, int n_cells, double r2, int* counts,
                      cudaStream_t st) {
@@ -431,7 +432,7 @@ void oi_launch_build(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, Oi
 }
 void oi_launch_chol_update(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int k, cudaStream_t st) {
     set_attrs();
-    k_chol_update<<<dim3(k == 0 ? 1 : Nmax - k, cnt_gt[k]), OI_THREADS, OI_SMEM_BYTES, st>>>(slots, k);
+    k_chol_update<<<dim3(k == 0 ? 1 : Nmax - k, cnt_gt[k]), OI_THREADS, OI_SMEM_PIPE, st>>>(slots, k);
 }
 void oi_launch_chol_panel(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int k, cudaStream_t st) {
     set_attrs();

@@ -238,13 +238,21 @@ __device__ __forceinline__ void gemm_nt_stream(double (&acc)[4][4][2], const dou
 // semantics, which is what np.linalg.cholesky runs), every other sub-block operation (panel solve,
 // trailing update, inverse by block distance) is one or two DMMA m8n8k4 per 8x8 block.
 // ------------------------------------------------------------------------------------------
-// 8x8 pivot block (jb, jb) of T: Cholesky factor in place (lower) and its inverse into W, by one warp in registers
+// The diagonal 64x64 block lives in ONE shared-memory array P[64][TS]: the Cholesky factor L (lower triangle incl.
+// the diagonal) at P[r][c], c <= r, and its inverse W = L^-1 (also lower triangular) transposed into the strict upper
+// part shifted by one column: W(r, c) = P[c][r + 1], r >= c.  37 KB instead of two 35 KB arrays, so the kernel's
+// shared memory is the 48 KB operand pipeline and 4 CTAs fit an SM (the CTAs of diagonal tiles keep one warp busy
+// for ~20 us; more co-resident CTAs keep the DMMA pipe fed meanwhile).
+__device__ __forceinline__ double& Wat(double* P, int r, int c) { return P[c * TS + r + 1]; }                  // r >= c
+__device__ __forceinline__ double Wval(const double* P, int r, int c) { return c <= r ? P[c * TS + r + 1] : 0.0; }
+
+// 8x8 pivot block (jb, jb): Cholesky factor in place (lower) and its inverse, by one warp in registers
 // (lane r = row r; the four groups of 8 lanes do the same work).  dpotf2 order of operations.
-__device__ __forceinline__ void pivot_factor_invert(double* T, double* W, int jb, int lane, int* s_bad) {
+__device__ __forceinline__ void pivot_factor_invert(double* P, int jb, int lane, int* s_bad) {
     const int r = lane & 7;
     double a[8];
 #pragma unroll
-    for (int c = 0; c < 8; c++) a[c] = T[(jb + r) * TS + jb + c];
+    for (int c = 0; c < 8; c++) a[c] = P[(jb + r) * TS + jb + c];         // entries c > r are loaded but never used
     bool bad = false;
     double dinv[8];                                                  // 1 / L[c][c], known to every lane
 #pragma unroll
@@ -267,7 +275,7 @@ __device__ __forceinline__ void pivot_factor_invert(double* T, double* W, int jb
     }
     if (lane < 8) {
 #pragma unroll
-        for (int c = 0; c < 8; c++) if (c <= r) T[(jb + r) * TS + jb + c] = a[c];
+        for (int c = 0; c < 8; c++) if (c <= r) P[(jb + r) * TS + jb + c] = a[c];
     }
     __syncwarp();
     // X = L8^-1, lane b owns column b:  x[rr] = -(sum_{l<rr} L[rr][l] x[l]) / L[rr][rr]
@@ -277,12 +285,12 @@ __device__ __forceinline__ void pivot_factor_invert(double* T, double* W, int jb
     for (int rr = 0; rr < 8; rr++) {
         double sacc = 0.0;
 #pragma unroll
-        for (int l = 0; l < rr; l++) sacc = fma(T[(jb + rr) * TS + jb + l], x[l], sacc);
+        for (int l = 0; l < rr; l++) sacc = fma(P[(jb + rr) * TS + jb + l], x[l], sacc);
         x[rr] = (rr < b) ? 0.0 : ((rr == b) ? dinv[rr] : -sacc * dinv[rr]);
     }
     if (lane < 8) {
 #pragma unroll
-        for (int rr = 0; rr < 8; rr++) if (rr >= b) W[(jb + rr) * TS + jb + b] = x[rr];
+        for (int rr = 0; rr < 8; rr++) if (rr >= b) Wat(P, jb + rr, jb + b) = x[rr];
     }
 }
 
@@ -300,38 +308,40 @@ __device__ __forceinline__ void diag_trailing_block(double* T, int i, int l, int
 
 // The 64 pivots are one dependent chain run by warp 0 (the critical path of the kernel's diagonal CTAs), so the
 // chain is overlapped with the DMMA work: after the panel of step j, warp 0 updates only the next pivot block and
-// factors it (look-ahead) while warps 1-3 apply the rest of step j's trailing update.
-__device__ __forceinline__ void diag_factor_invert(double* T, double* W, double* sc, int* s_bad, int tid) {
+// factors it (look-ahead) while warps 1-3 apply the rest of step j's trailing update.  (The trailing update of an
+// 8x8 diagonal sub-block (l == i, i > j+1) also rewrites that sub-block's strict upper part: it holds no W yet --
+// X_ii is written when block i becomes the pivot -- and nothing reads it.)
+__device__ __forceinline__ void diag_factor_invert(double* P, double* sc, int* s_bad, int tid) {
     const int warp = tid >> 5, lane = tid & 31, fr = lane >> 2, fc = lane & 3;
-    if (warp == 0) pivot_factor_invert(T, W, 0, lane, s_bad);
+    if (warp == 0) pivot_factor_invert(P, 0, lane, s_bad);
     __syncthreads();
     if (*s_bad) return;
     for (int j = 0; j < 8; j++) {
         const int jb = j * 8;
-        // panel: L_ij = A_ij * X_jj^T  (i > j)
+        // panel: L_ij = A_ij * X_jj^T  (i > j); X_jj[n][k] = W(jb+n, jb+k), zero for k > n
         for (int i = j + 1 + warp; i < 8; i += 4) {
             double c2[2] = {0.0, 0.0};
 #pragma unroll
             for (int ks = 0; ks < 2; ks++)
-                dmma(c2, T[(i * 8 + fr) * TS + jb + ks * 4 + fc], W[(jb + fr) * TS + jb + ks * 4 + fc]);
+                dmma(c2, P[(i * 8 + fr) * TS + jb + ks * 4 + fc], Wval(P, jb + fr, jb + ks * 4 + fc));
             __syncwarp();
-            T[(i * 8 + fr) * TS + jb + fc * 2] = c2[0];
-            T[(i * 8 + fr) * TS + jb + fc * 2 + 1] = c2[1];
+            P[(i * 8 + fr) * TS + jb + fc * 2] = c2[0];
+            P[(i * 8 + fr) * TS + jb + fc * 2 + 1] = c2[1];
         }
         __syncthreads();
         if (j == 7) break;
         // trailing update: A_il -= L_ij L_lj^T  (j < l <= i); block q = 0 is the next pivot block (j+1, j+1)
         const int m = 7 - j, cnt = m * (m + 1) / 2;
         if (warp == 0) {
-            diag_trailing_block(T, j + 1, j + 1, jb, fr, fc);
+            diag_trailing_block(P, j + 1, j + 1, jb, fr, fc);
             __syncwarp();
-            pivot_factor_invert(T, W, jb + 8, lane, s_bad);
+            pivot_factor_invert(P, jb + 8, lane, s_bad);
         } else {
             for (int q = warp; q < cnt; q += 3) {
                 int ii = 0;                                   // q -> (ii, ll), ll <= ii, integer only (cnt <= 28)
                 while ((ii + 1) * (ii + 2) / 2 <= q) ii++;
                 const int ll = q - ii * (ii + 1) / 2;
-                diag_trailing_block(T, j + 1 + ii, j + 1 + ll, jb, fr, fc);
+                diag_trailing_block(P, j + 1 + ii, j + 1 + ll, jb, fr, fc);
             }
         }
         __syncthreads();
@@ -344,18 +354,18 @@ __device__ __forceinline__ void diag_factor_invert(double* T, double* W, double*
             double c1[2] = {0.0, 0.0};
             for (int jj = kb; jj < i; jj++) {
 #pragma unroll
-                for (int ks = 0; ks < 2; ks++)
-                    dmma(c1, T[(i * 8 + fr) * TS + jj * 8 + ks * 4 + fc], W[(jj * 8 + ks * 4 + fc) * TS + kb * 8 + fr]);
+                for (int ks = 0; ks < 2; ks++)         // B[k][n] = W(jj*8+k, kb*8+n): lower triangular when jj == kb
+                    dmma(c1, P[(i * 8 + fr) * TS + jj * 8 + ks * 4 + fc], Wval(P, jj * 8 + ks * 4 + fc, kb * 8 + fr));
             }
             sc[fr * 8 + fc * 2] = c1[0];
             sc[fr * 8 + fc * 2 + 1] = c1[1];
             __syncwarp();
             double c2[2] = {0.0, 0.0};
 #pragma unroll
-            for (int ks = 0; ks < 2; ks++)
-                dmma(c2, W[(i * 8 + fr) * TS + i * 8 + ks * 4 + fc], sc[(ks * 4 + fc) * 8 + fr]);
-            W[(i * 8 + fr) * TS + kb * 8 + fc * 2] = -c2[0];
-            W[(i * 8 + fr) * TS + kb * 8 + fc * 2 + 1] = -c2[1];
+            for (int ks = 0; ks < 2; ks++)             // A[m][k] = X_ii[m][k] = W(i*8+m, i*8+k), zero for k > m
+                dmma(c2, Wval(P, i * 8 + fr, i * 8 + ks * 4 + fc), sc[(ks * 4 + fc) * 8 + fr]);
+            Wat(P, i * 8 + fr, kb * 8 + fc * 2) = -c2[0];
+            Wat(P, i * 8 + fr, kb * 8 + fc * 2 + 1) = -c2[1];
             __syncwarp();
         }
         __syncthreads();
@@ -367,7 +377,7 @@ __device__ __forceinline__ void diag_factor_invert(double* T, double* W, double*
 // the CTA of the diagonal tile then factors it in shared memory (dpotrf semantics: a pivot
 // <= 0 raises the cell's fail flag), inverts the 64x64 factor and stores
 //   Dinv[k] = L_kk^-1 (row-major)   and   M(k,k) = U_kk = L_kk^-T (upper, zeros below).
-// smem: OI_SMEM_BYTES.
+// smem: PIPE_BYTES (the packed diagonal block needs 37 KB of it).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tile_chol_update(const OiSlot& s, int i, int k, double* smem) {
     const long long ld = s.npad;
@@ -404,30 +414,28 @@ __device__ __forceinline__ void tile_chol_update(const OiSlot& s, int i, int k, 
             }
         return;
     }
-    // ---- diagonal tile: T = A_kk - acc, factor + invert in shared memory ----
-    double* T = smem;                    // [64][TS]  A_kk -> L_kk (lower)
-    double* W = smem + NB * TS;          // [64][TS]  L_kk^-1 (lower, zeros above)
-    double* sc = smem + 2 * NB * TS + warp * 64;   // per-warp 8x8 scratch
-    int* s_bad = (int*)(smem + 2 * NB * TS + 4 * 64);
+    // ---- diagonal tile: P = A_kk - acc, factor + invert in shared memory (packed L / W layout, see above) ----
+    double* P = smem;                          // [64][TS]
+    double* sc = smem + NB * TS + warp * 64;   // per-warp 8x8 scratch
+    int* s_bad = (int*)(smem + NB * TS + 4 * 64);
 #pragma unroll
     for (int mb = 0; mb < 4; mb++)
 #pragma unroll
         for (int nb = 0; nb < 4; nb++) {
             int r = FRAG_ROW(wm, mb, lane), c = FRAG_COL(wn, nb, lane);
-            T[r * TS + c] = cin[mb][nb].x - acc[mb][nb][0];
-            T[r * TS + c + 1] = cin[mb][nb].y - acc[mb][nb][1];
+            P[r * TS + c] = cin[mb][nb].x - acc[mb][nb][0];
+            P[r * TS + c + 1] = cin[mb][nb].y - acc[mb][nb][1];
         }
-    for (int idx = tid; idx < NB * TS; idx += GEMM_THREADS) W[idx] = 0.0;
     if (tid == 0) *s_bad = 0;
     __syncthreads();
-    diag_factor_invert(T, W, sc, s_bad, tid);
+    diag_factor_invert(P, sc, s_bad, tid);
     if (*s_bad) {
         if (tid == 0) *s.fail = 1;
         return;
     }
     if (warp == 0) {
         // log-determinant part: sum_i log L_ii of this block (GPR_CS2S3.py:128), fixed order
-        double v = log(T[lane * TS + lane]) + log(T[(lane + 32) * TS + lane + 32]);
+        double v = log(P[lane * TS + lane]) + log(P[(lane + 32) * TS + lane + 32]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (lane == 0) s.part[k] = v;
@@ -435,8 +443,8 @@ __device__ __forceinline__ void tile_chol_update(const OiSlot& s, int i, int k, 
     double* Dk = s.Dinv + (long long)k * OI_TILE;
     for (int idx = tid; idx < OI_TILE; idx += GEMM_THREADS) {
         int r = idx >> 6, c = idx & 63;
-        Dk[idx] = W[r * TS + c];
-        Cg[(long long)r * ld + c] = (c >= r) ? W[c * TS + r] : 0.0;
+        Dk[idx] = Wval(P, r, c);                                   // Dinv[k] = L_kk^-1, row-major, zeros above the diagonal
+        Cg[(long long)r * ld + c] = Wval(P, c, r);                 // U_kk = L_kk^-T: upper triangular, zeros below
     }
 }
 
