@@ -274,10 +274,10 @@ static int ensure_batch_buffers(oi_handle* h, size_t want_arena, int want_slots,
     if (!h->d_tickets) CK(cudaMalloc(&h->d_tickets, 16 * 32 * 4));      // one ticket counter per group, 128 B apart
     while ((int)h->groups.size() < G) {
         OiGroup* g = new OiGroup();
+        h->groups.push_back(g);                       // owned by the handle from here on (freed in free_groups)
         CK(cudaStreamCreateWithFlags(&g->st, cudaStreamNonBlocking));
         for (auto& e : g->ev) CK(cudaEventCreate(&e));
         CK(cudaEventCreateWithFlags(&g->done, cudaEventDisableTiming));
-        h->groups.push_back(g);
     }
     return OI_OK;
 }
@@ -416,8 +416,10 @@ struct LockstepRun {
                 if (g.same_count >= 2) {
                     cudaGraph_t graph = nullptr;
                     CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-                    launch_chain(g, A, Nmax, cg, st, false);
-                    CK(cudaStreamEndCapture(st, &graph));
+                    const int lr = launch_chain(g, A, Nmax, cg, st, false);
+                    cudaError_t ce = cudaStreamEndCapture(st, &graph);      // always leave capture mode
+                    if (lr) { if (graph) cudaGraphDestroy(graph); return lr; }
+                    CK(ce);
                     if (g.gexec) { cudaGraphExecDestroy(g.gexec); g.gexec = nullptr; }
                     CK(cudaGraphInstantiate(&g.gexec, graph, 0));
                     cudaGraphDestroy(graph);
