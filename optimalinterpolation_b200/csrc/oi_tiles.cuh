@@ -1,7 +1,7 @@
 // Tile-level device functions of the per-cell GP hot path.  Every function is executed
 // by ONE CTA of OI_THREADS (128) threads on one 64x64 tile (or one cell for the substitutions) and is shared
 // by the two execution engines:
-//   * the persistent group kernel  (oi_persist.cu): a group of CTAs walks one cell through a whole
+//   * the persistent group kernel  (oi_kernels.cu: k_gp_persistent): a group of CTAs walks one cell through a whole
 //     NLML+gradient evaluation, synchronising through a global-memory group barrier;
 //   * the lockstep launch-per-step kernels (oi_kernels.cu): one launch per algorithmic step over all cells.
 // Both engines therefore produce bit-identical numbers (fixed reduction orders, no atomics on data).
