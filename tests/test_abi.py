@@ -64,3 +64,24 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".h", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/oi_b200.h must compile as C (no C++/torch types in the boundary) and a C program linked against the
+    shared library must run the calls that need no GPU."""
+    import subprocess
+    from optimalinterpolation_b200 import _lib
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "oi_b200.h"\n'
+                   'int main(void) {\n'
+                   '  oi_params p = {0}; oi_stats s; (void)s; p.mode = OI_MODE_FIT; p.engine = OI_ENGINE_LOCKSTEP;\n'
+                   '  printf("%d %d %d\\n", oi_version(), oi_sizeof_params() == (int)sizeof(oi_params), oi_sizeof_stats() == (int)sizeof(oi_stats));\n'
+                   '  return oi_run(NULL, &p, NULL) == OI_ERR_ARG ? 0 : 1;\n}\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-loi_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    ver, okp, oks = out.stdout.split()
+    assert int(ver) >= 110 and okp == "1" and oks == "1"
