@@ -8,6 +8,7 @@
  *   reference                                          this ABI
  *   ---------                                          --------
  *   x_train,y_train,t_train,z  (:238-241)              oi_set_observations()
+ *   sat = obs[:,:,:,day:day+T] (:213)                  oi_set_time_window() on a resident season (optional)
  *   X = ice-cell coordinates   (:244)                  oi_set_cells()
  *   X_tree.query_ball_point    (:159, :245-246)        oi_gather_neighbours() / oi_get_neighbours()
  *   SMLII(hypers, x, y, mX)    (:107-141)              oi_nlml_grad()
@@ -108,6 +109,12 @@ void oi_destroy(oi_handle* h);
 /* Observations of the day window: x_train, y_train, t_train, z (GPR_CS2S3.py:238-241). */
 int oi_set_observations(oi_handle* h, const double* x, const double* y, const double* t, const double* z,
                         int64_t n_obs);
+/* Day window of the neighbour gather: only observations with t_lo <= t <= t_hi take part, and their time coordinate
+ * is counted from t_lo (the reference slices obs[:, :, :, day:day+T] and numbers the days of the window 0..T-1,
+ * GPR_CS2S3.py:213, :227-235).  With it a whole season of flattened observations (stream-major, day-major, row-major,
+ * t = absolute day index) stays resident and every day only moves the window: oi_set_time_window(h, day, day+T-1).
+ * Default: no window (-inf, +inf), t used as given. */
+int oi_set_time_window(oi_handle* h, double t_lo, double t_hi);
 /* Target cells X[n_cells][2] (GPR_CS2S3.py:244). */
 int oi_set_cells(oi_handle* h, const double* X, int64_t n_cells);
 

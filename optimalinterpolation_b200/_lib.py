@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "liboi_b200.so")
 
 EXPORTS = ("oi_version", "oi_last_error", "oi_create", "oi_destroy", "oi_set_observations", "oi_set_cells",
            "oi_gather_neighbours", "oi_get_neighbours", "oi_nlml_grad", "oi_run", "oi_get_results",
-           "oi_get_stats", "oi_gpr_day", "oi_set_stream", "oi_sizeof_params", "oi_sizeof_stats")
+           "oi_get_stats", "oi_gpr_day", "oi_set_stream", "oi_sizeof_params", "oi_sizeof_stats", "oi_set_time_window")
 
 
 class OiParams(C.Structure):
@@ -66,6 +66,7 @@ def load():
     L.oi_destroy.restype = None
     L.oi_set_observations.argtypes = [vp, dp, dp, dp, dp, C.c_int64]
     L.oi_set_cells.argtypes = [vp, dp, C.c_int64]
+    L.oi_set_time_window.argtypes = [vp, C.c_double, C.c_double]
     L.oi_gather_neighbours.argtypes = [vp, C.c_double, ip]
     L.oi_get_neighbours.argtypes = [vp, lp, ip]
     L.oi_nlml_grad.argtypes = [vp, dp, C.c_int32, C.c_double, C.c_int32, dp, dp]

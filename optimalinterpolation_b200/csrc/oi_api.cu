@@ -33,6 +33,7 @@ struct oi_handle {
     // observations
     double *ox = nullptr, *oy = nullptr, *ot = nullptr, *oz = nullptr;
     int64_t n_obs = 0, obs_cap = 0;
+    double t_lo = -INFINITY, t_hi = INFINITY, t_shift = 0.0;      // day window of the gather (oi_set_time_window)
     // cells
     double* X = nullptr;
     int64_t n_cells = 0, cell_cap = 0;
@@ -159,6 +160,13 @@ extern "C" int oi_set_observations(oi_handle* h, const double* x, const double* 
     return OI_OK;
 }
 
+extern "C" int oi_set_time_window(oi_handle* h, double t_lo, double t_hi) {
+    if (!h || !(t_lo <= t_hi)) return fail(OI_ERR_ARG, "oi_set_time_window: need t_lo <= t_hi");
+    h->t_lo = t_lo; h->t_hi = t_hi; h->t_shift = std::isfinite(t_lo) ? t_lo : 0.0;
+    h->have_nbr = false; h->have_results = false;
+    return OI_OK;
+}
+
 extern "C" int oi_set_cells(oi_handle* h, const double* X, int64_t n_cells) {
     if (!h || !X || n_cells <= 0 || n_cells > 0x3fffffff) return fail(OI_ERR_ARG, "oi_set_cells: bad argument");
     CK(cudaSetDevice(h->device));
@@ -186,7 +194,7 @@ extern "C" int oi_gather_neighbours(oi_handle* h, double radius_m, int32_t* coun
     const double r2 = radius_m * radius_m;
     const int nc = (int)h->n_cells, no = (int)h->n_obs;
     CK(cudaEventRecord(h->ev[8], h->st));
-    oi_launch_count(h->ox, h->oy, no, h->X, nc, r2, h->counts, h->st);
+    oi_launch_count(h->ox, h->oy, h->ot, no, h->X, nc, r2, h->t_lo, h->t_hi, h->counts, h->st);
     oi_launch_scan(h->counts, nc, h->offsets, h->st);
     CK(cudaGetLastError());
     long long total = 0;
@@ -204,7 +212,7 @@ extern "C" int oi_gather_neighbours(oi_handle* h, double radius_m, int32_t* coun
     h->total = total;
     h->h_offsets.assign((size_t)nc + 1, 0);
     for (int c = 0; c < nc; c++) h->h_offsets[c + 1] = h->h_offsets[c] + h->h_counts[c];
-    if (total > 0) oi_launch_fill(h->ox, h->oy, no, h->X, nc, r2, h->offsets, h->indices, h->st);
+    if (total > 0) oi_launch_fill(h->ox, h->oy, h->ot, no, h->X, nc, r2, h->t_lo, h->t_hi, h->offsets, h->indices, h->st);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[9], h->st));
     CK(cudaStreamSynchronize(h->st));
@@ -745,7 +753,7 @@ static int engine_from_env(int engine) {
 }
 
 static int pack_points(oi_handle* h, double mean) {
-    oi_launch_pack(h->indices, h->total, h->ox, h->oy, h->ot, h->oz, mean, h->px, h->py, h->pt, h->pr, h->st);
+    oi_launch_pack(h->indices, h->total, h->ox, h->oy, h->ot, h->oz, mean, h->t_shift, h->px, h->py, h->pt, h->pr, h->st);
     CK(cudaGetLastError());
     return OI_OK;
 }

@@ -17,13 +17,14 @@
 // kernel (1): neighbour gather.  One warp per cell, observations staged through shared memory
 // in chunks shared by the 8 cells of the CTA; ordered compaction by ballot + popc prefix.
 // ------------------------------------------------------------------------------------------
-#define G_CHUNK 2048
+#define G_CHUNK 1024
 template <bool FILL>
-__global__ void __launch_bounds__(256) k_gather(const double* __restrict__ ox, const double* __restrict__ oy, int n_obs,
-                                                const double* __restrict__ X, int n_cells, double r2,
+__global__ void __launch_bounds__(256) k_gather(const double* __restrict__ ox, const double* __restrict__ oy,
+                                                const double* __restrict__ ot, int n_obs,
+                                                const double* __restrict__ X, int n_cells, double r2, double t_lo, double t_hi,
                                                 int* __restrict__ counts, const long long* __restrict__ offsets,
                                                 int* __restrict__ indices) {
-    __shared__ double sx[G_CHUNK], sy[G_CHUNK];
+    __shared__ double sx[G_CHUNK], sy[G_CHUNK], st[G_CHUNK];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cell = blockIdx.x * 8 + warp;
     const bool live = cell < n_cells;
@@ -35,7 +36,7 @@ __global__ void __launch_bounds__(256) k_gather(const double* __restrict__ ox, c
     for (int c0 = 0; c0 < n_obs; c0 += G_CHUNK) {
         int m = min(G_CHUNK, n_obs - c0);
         __syncthreads();
-        for (int q = threadIdx.x; q < m; q += 256) { sx[q] = ox[c0 + q]; sy[q] = oy[c0 + q]; }
+        for (int q = threadIdx.x; q < m; q += 256) { sx[q] = ox[c0 + q]; sy[q] = oy[c0 + q]; st[q] = ot[c0 + q]; }
         __syncthreads();
         if (live) {
             for (int q0 = 0; q0 < m; q0 += 32) {
@@ -43,8 +44,9 @@ __global__ void __launch_bounds__(256) k_gather(const double* __restrict__ ox, c
                 bool in = false;
                 if (q < m) {
                     double dx = sx[q] - cx, dy = sy[q] - cy;
-                    // inclusive boundary, no FMA: ties on the 25 km lattice resolve as in the reference (GPR_CS2S3.py:159)
-                    in = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= r2;
+                    // inclusive boundary, no FMA: ties on the 25 km lattice resolve as in the reference (GPR_CS2S3.py:159);
+                    // the day window [t_lo, t_hi] (inclusive; +-inf = off) is the reference's obs[..., day:day+T] (:213)
+                    in = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= r2 && st[q] >= t_lo && st[q] <= t_hi;
                 }
                 unsigned bal = __ballot_sync(0xffffffffu, in);
                 if (FILL && in) indices[base + cnt + __popc(bal & ((1u << lane) - 1u))] = c0 + q;
@@ -76,12 +78,14 @@ __global__ void k_scan_counts(const int* __restrict__ counts, int n, long long* 
 
 __global__ void k_pack(const int* __restrict__ indices, long long total, const double* __restrict__ ox,
                        const double* __restrict__ oy, const double* __restrict__ ot, const double* __restrict__ oz,
-                       double mean, double* __restrict__ px, double* __restrict__ py, double* __restrict__ pt,
+                       double mean, double t_shift, double* __restrict__ px, double* __restrict__ py, double* __restrict__ pt,
                        double* __restrict__ pr) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     int id = indices[i];
-    px[i] = ox[id]; py[i] = oy[id]; pt[i] = ot[id]; pr[i] = oz[id] - mean;   // outputs - mX (GPR_CS2S3.py:127)
+    // t counts from the start of the day window (the reference's t_train is the day index inside the window, :227-235);
+    // outputs - mX (GPR_CS2S3.py:127)
+    px[i] = ox[id]; py[i] = oy[id]; pt[i] = ot[id] - t_shift; pr[i] = oz[id] - mean;
 }
 
 
@@ -403,21 +407,21 @@ static_assert(OI_SMEM_PIPE == PIPE_BYTES, "pipeline size");
 static_assert(OI_SMEM_BYTES >= PIPE_BYTES && OI_SMEM_BYTES >= 2 * NB * TS * 8 + 4 * 64 * 8 + 16, "shared memory budget");
 static_assert(PIPE_BYTES >= NB * TS * 8 + 4 * 64 * 8 + 16, "packed diagonal block must fit the pipeline buffers");
 
-void oi_launch_count(const double* ox, const double* oy, int n_obs, const double* X, int n_cells, double r2, int* counts,
-                     cudaStream_t st) {
-    k_gather<false><<<(n_cells + 7) / 8, 256, 0, st>>>(ox, oy, n_obs, X, n_cells, r2, counts, nullptr, nullptr);
+void oi_launch_count(const double* ox, const double* oy, const double* ot, int n_obs, const double* X, int n_cells, double r2,
+                     double t_lo, double t_hi, int* counts, cudaStream_t st) {
+    k_gather<false><<<(n_cells + 7) / 8, 256, 0, st>>>(ox, oy, ot, n_obs, X, n_cells, r2, t_lo, t_hi, counts, nullptr, nullptr);
 }
 void oi_launch_scan(const int* counts, int n, long long* offsets, cudaStream_t st) {
     k_scan_counts<<<1, 1024, 0, st>>>(counts, n, offsets);
 }
-void oi_launch_fill(const double* ox, const double* oy, int n_obs, const double* X, int n_cells, double r2,
-                    const long long* offsets, int* indices, cudaStream_t st) {
-    k_gather<true><<<(n_cells + 7) / 8, 256, 0, st>>>(ox, oy, n_obs, X, n_cells, r2, nullptr, offsets, indices);
+void oi_launch_fill(const double* ox, const double* oy, const double* ot, int n_obs, const double* X, int n_cells, double r2,
+                    double t_lo, double t_hi, const long long* offsets, int* indices, cudaStream_t st) {
+    k_gather<true><<<(n_cells + 7) / 8, 256, 0, st>>>(ox, oy, ot, n_obs, X, n_cells, r2, t_lo, t_hi, nullptr, offsets, indices);
 }
 void oi_launch_pack(const int* indices, long long total, const double* ox, const double* oy, const double* ot,
-                    const double* oz, double mean, double* px, double* py, double* pt, double* pr, cudaStream_t st) {
+                    const double* oz, double mean, double t_shift, double* px, double* py, double* pt, double* pr, cudaStream_t st) {
     if (total <= 0) return;
-    k_pack<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(indices, total, ox, oy, ot, oz, mean, px, py, pt, pr);
+    k_pack<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(indices, total, ox, oy, ot, oz, mean, t_shift, px, py, pt, pr);
 }
 // Slots are sorted by descending size, so the cells that own block row/column x are the prefix cnt_gt[x]
 // (number of slots with N > x): every grid below is exact in the slot dimension.  Big batches launch

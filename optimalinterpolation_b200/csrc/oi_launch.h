@@ -18,13 +18,13 @@ struct OiRunConst {
     int n_hyp, grad_convention, maxiter;
     double x0[6];
 };
-void oi_launch_count(const double* ox, const double* oy, int n_obs, const double* X, int n_cells, double r2, int* counts,
-                     cudaStream_t st);
+void oi_launch_count(const double* ox, const double* oy, const double* ot, int n_obs, const double* X, int n_cells, double r2,
+                     double t_lo, double t_hi, int* counts, cudaStream_t st);
 void oi_launch_scan(const int* counts, int n, long long* offsets, cudaStream_t st);
-void oi_launch_fill(const double* ox, const double* oy, int n_obs, const double* X, int n_cells, double r2,
-                    const long long* offsets, int* indices, cudaStream_t st);
+void oi_launch_fill(const double* ox, const double* oy, const double* ot, int n_obs, const double* X, int n_cells, double r2,
+                    double t_lo, double t_hi, const long long* offsets, int* indices, cudaStream_t st);
 void oi_launch_pack(const int* indices, long long total, const double* ox, const double* oy, const double* ot,
-                    const double* oz, double mean, double* px, double* py, double* pt, double* pr, cudaStream_t st);
+                    const double* oz, double mean, double t_shift, double* px, double* py, double* pt, double* pr, cudaStream_t st);
 void oi_launch_build(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, OiCellArrays ca, OiPacked pk, cudaStream_t st);
 void oi_launch_chol_update(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int k, cudaStream_t st);
 void oi_launch_chol_fused(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int* ticket, cudaStream_t st);

@@ -66,6 +66,11 @@ class Handle:
         self._check(self._L.oi_set_observations(self._h, _ptr(x), _ptr(y), _ptr(t), _ptr(z), x.size))
         self.n_obs = x.size
 
+    def set_time_window(self, t_lo: float = -np.inf, t_hi: float = np.inf):
+        """Only observations with t_lo <= t <= t_hi take part in the gather; t then counts from t_lo (the reference's
+        ``obs[:, :, :, day:day+T]`` window, GPR_CS2S3.py:213).  No arguments: window off."""
+        self._check(self._L.oi_set_time_window(self._h, float(t_lo), float(t_hi)))
+
     def set_cells(self, X):
         X = _f64(X)
         if X.ndim != 2 or X.shape[1] != 2:

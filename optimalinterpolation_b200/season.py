@@ -4,8 +4,11 @@ The reference script processes ONE hard-coded day (``day = 1``, :211): it slices
 season's gridded observations (:213), flattens it stream-major / day-major / row-major into ``x_train, y_train,
 t_train, z`` (:223-241), takes the ice cells of the middle day (:214, :243-244) and a prior mean (:212), and then
 runs both passes.  ``run_season`` repeats exactly that setup for a list of days on one resident GPU handle.
-Everything here is O(grid) host work; a day's flattened observations are ~1 MB, so keeping the whole season
-resident on the device would buy nothing - the window is rebuilt on the host and uploaded by ``oi_gpr_day``.
+Everything here is O(grid) host work.  Two ways to feed the GPU: per day (the window is flattened on the host and
+uploaded by ``oi_gpr_day``, ~1 MB) or ``resident=True``: the whole season is flattened once (``flatten_season``, same
+stream-major / day-major / row-major order with the absolute day index as t), stays on the device, and each day only
+moves the gather's day window (``oi_set_time_window``) - the neighbour lists, their order and the window-relative
+time coordinate are the same, so both ways give bit-identical results.
 """
 from __future__ import annotations
 
@@ -34,6 +37,29 @@ def flatten_window(obs: np.ndarray, x: np.ndarray, y: np.ndarray, day: int, T: i
             np.concatenate(ts).astype(np.float64), np.concatenate(zs).astype(np.float64))
 
 
+def flatten_season(obs: np.ndarray, x: np.ndarray, y: np.ndarray):
+    """All days of ``obs`` flattened like a window (:223-241) with t = absolute day index: restricting it to
+    day <= t <= day+T-1 leaves exactly ``flatten_window(obs, x, y, day, T)`` (same order, t shifted by ``day``)."""
+    return flatten_window(obs, x, y, 0, obs.shape[3])
+
+
+class _ResidentDay:
+    """``GPRDay``-like front end (what ``postprocess.two_pass`` needs) on a handle that already holds the season's
+    observations: selects the day window, uploads the day's cells and gathers once, then runs either pass."""
+
+    def __init__(self, handle: Handle, day: int, T: int, X, radius, mean, T_mid, x0):
+        self.handle, self.radius, self.mean, self.T_mid, self.x0 = handle, float(radius), float(mean), float(T_mid), list(x0)
+        handle.set_time_window(day, day + T - 1)
+        handle.set_cells(X)
+        handle.gather_neighbours(self.radius * 1000.0)
+
+    def run(self, opt: bool = True, ellXs=None, sf2xs=None, sn2xs=None, **kw):
+        hin = None if opt else np.column_stack([np.asarray(ellXs, float), np.asarray(sf2xs, float), np.asarray(sn2xs, float)])
+        p = self.handle.make_params(self.radius * 1000.0, self.T_mid, self.mean, self.x0, mode=0 if opt else 1, **kw)
+        self.handle.run(p, hin)
+        return self.handle.get_results()
+
+
 def day_inputs(obs, sie_mask, x, y, day: int, T: int = 9, prior_mean=None) -> dict:
     """The module globals of GPR_CS2S3.py:207-246 for one day index (the interpolated day is day + T//2).
 
@@ -58,7 +84,7 @@ def day_inputs(obs, sie_mask, x, y, day: int, T: int = 9, prior_mean=None) -> di
 
 def run_season(obs, sie_mask, x, y, days, dates=None, grid_res: float = 25, T: int = 9, radius: float = 300,
                x0=None, prior_mean=None, smooth_pass: bool = True, device: int = 0, handle: Handle | None = None,
-               **run_kw) -> dict:
+               resident: bool = False, **run_kw) -> dict:
     """Both passes (or pass 1 only) for every day index in ``days`` on one GPU handle.
 
     Returns one dict with the reference's per-date keys (``<date>_interp``, ``<date>_ell_x_smth``, ...,
@@ -69,11 +95,16 @@ def run_season(obs, sie_mask, x, y, days, dates=None, grid_res: float = 25, T: i
     handle = handle or Handle(device)
     out = {}
     try:
+        if resident:
+            handle.set_observations(*flatten_season(obs, x, y))          # once; every day only moves the window
         for day in days:
             g = day_inputs(obs, sie_mask, x, y, day, T, prior_mean)
             date = str(dates[day + g["T_mid"]]) if dates is not None else str(day + g["T_mid"])
-            gd = GPRDay(g["x_train"], g["y_train"], g["t_train"], g["z"], g["X"], radius, g["mean"], g["T_mid"], x0,
-                        handle=handle)
+            if resident:
+                gd = _ResidentDay(handle, day, T, g["X"], radius, g["mean"], g["T_mid"], x0)
+            else:
+                gd = GPRDay(g["x_train"], g["y_train"], g["t_train"], g["z"], g["X"], radius, g["mean"], g["T_mid"], x0,
+                            handle=handle)
             if smooth_pass:
                 res = two_pass(gd, g["ids"], g["SIE"].shape, g["SIE"], date=date, grid_res=grid_res, T=T, **run_kw)
                 res[date + "_diagnostics"] = res.pop("_diagnostics")
@@ -82,6 +113,8 @@ def run_season(obs, sie_mask, x, y, days, dates=None, grid_res: float = 25, T: i
                 res = assemble(r1["out"], g["ids"], g["SIE"].shape, date)
             out.update(res)
     finally:
+        if resident and not own:
+            handle.set_time_window()                                      # leave a borrowed handle without a window
         if own:
             handle.close()
     return out

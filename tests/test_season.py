@@ -40,6 +40,45 @@ def test_flatten_window_matches_reference_loop():
     assert day_inputs(obs, sie, x, y, 2, 9, prior_mean=lambda d: 0.1 * d)["mean"] == 0.2
 
 
+def test_flatten_season_restricted_to_a_window_is_the_window():
+    from optimalinterpolation_b200.season import flatten_window, flatten_season
+    obs, sie, x, y = _small_season()
+    xs, ys, ts, zs = flatten_season(obs, x, y)
+    for day in (0, 1, 2):
+        m = (ts >= day) & (ts <= day + 8)
+        xw, yw, tw, zw = flatten_window(obs, x, y, day, 9)
+        assert np.array_equal(xs[m], xw) and np.array_equal(ys[m], yw) and np.array_equal(zs[m], zw)
+        assert np.array_equal(ts[m] - day, tw)
+
+
+@pytest.mark.gpu
+def test_resident_season_equals_per_day_upload():
+    """Season observations resident on the device + day window in the gather kernel == flattening and uploading every
+    day's window: identical neighbour lists (after mapping the indices) and bit-identical results of both passes."""
+    import optimalinterpolation_b200 as oi
+    from optimalinterpolation_b200.season import run_season, flatten_season, flatten_window, day_inputs
+    obs, sie, x, y = _small_season()
+    a = run_season(obs, sie, x, y, days=[0, 2], radius=100, resident=True)
+    b = run_season(obs, sie, x, y, days=[0, 2], radius=100, resident=False)
+    assert set(a) == set(b)
+    for k in b:
+        if k.endswith("_diagnostics"):
+            assert np.array_equal(a[k]["nfev"], b[k]["nfev"]) and np.array_equal(a[k]["status"], b[k]["status"])
+        else:
+            assert np.array_equal(a[k], b[k], equal_nan=True), k
+    # neighbour lists: the windowed gather returns season indices; mapped to window positions they are the window's lists
+    xs, ys, ts, zs = flatten_season(obs, x, y)
+    g = day_inputs(obs, sie, x, y, 2, 9)
+    h = oi.Handle(0)
+    h.set_observations(xs, ys, ts, zs); h.set_time_window(2, 10); h.set_cells(g["X"]); h.gather_neighbours(100e3)
+    off_s, idx_s = h.get_neighbours()
+    h.set_time_window(); h.set_observations(*flatten_window(obs, x, y, 2, 9)); h.set_cells(g["X"]); h.gather_neighbours(100e3)
+    off_w, idx_w = h.get_neighbours()
+    pos = np.cumsum((ts >= 2) & (ts <= 10)) - 1              # season index -> position inside the window
+    assert np.array_equal(off_s, off_w) and np.array_equal(pos[idx_s], idx_w)
+    h.close()
+
+
 @pytest.mark.gpu
 def test_run_season_equals_day_by_day():
     """Two days on one resident handle give exactly what two independent GPRDay runs give (handle reuse across
