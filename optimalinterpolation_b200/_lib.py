@@ -19,7 +19,7 @@ class OiParams(C.Structure):
                 ("n_hyp", C.c_int32), ("mode", C.c_int32), ("grad_convention", C.c_int32), ("maxiter", C.c_int32),
                 ("x0", C.c_double * 6), ("gtol", C.c_double), ("scratch_gib", C.c_double),
                 ("max_active", C.c_int32), ("n_groups", C.c_int32), ("engine", C.c_int32), ("group_size", C.c_int32),
-                ("evals_per_launch", C.c_int32), ("reserved", C.c_int32)]
+                ("evals_per_launch", C.c_int32), ("optimiser", C.c_int32)]
 
 
 class OiStats(C.Structure):

@@ -16,6 +16,7 @@
 #include "oi_types.h"
 #include "oi_launch.h"
 #include "cg_scipy.h"
+#include "lbfgs_fast.h"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -50,15 +51,10 @@ struct oi_handle {
     // lockstep batch
     char* arena = nullptr; size_t arena_bytes = 0;
     OiSlot* d_slots = nullptr; OiSlot* h_slots = nullptr;
-    int *d_slot_phase = nullptr, *h_slot_phase = nullptr, *d_fail = nullptr, *d_tickets = nullptr;
+    int *d_slot_phase = nullptr, *h_slot_phase = nullptr, *d_fail = nullptr;
     int slot_cap = 0;
     cudaEvent_t ev[10]{};
     std::vector<struct OiGroup*> groups;
-    // persistent engine
-    OiWork* d_work = nullptr; OiWork* h_work = nullptr; int work_cap = 0;
-    OiGroupCtl* d_ctl = nullptr; int* d_pfail = nullptr; int* d_queue = nullptr; OiPersistAcc* d_acc = nullptr; int ctl_cap = 0;
-    int* h_phase_pinned = nullptr; int64_t phase_cap = 0;
-    int persist_capacity = 0;
     oi_stats stats{};
     bool have_results = false;
 };
@@ -74,20 +70,18 @@ static size_t slot_bytes(int n) {
     b += align_up(3 * npad * 8, 256);
     b += align_up((N + 8 + 5 * N * (N + 1) / 2) * 8, 256);
     b += align_up(N * (N + 1) / 2 * 2 * OI_TILE * 8, 256);      // Q and exp(-Q) tiles
-    b += align_up(2 * N * 4, 256);                                // dependency flags of the fused Cholesky
     return b;
 }
 
-extern "C" int oi_version(void) { return 110; }
+extern "C" int oi_version(void) { return 120; }
 extern "C" int oi_sizeof_params(void) { return (int)sizeof(oi_params); }
 extern "C" int oi_sizeof_stats(void) { return (int)sizeof(oi_stats); }
 extern "C" const char* oi_last_error(void) { return g_err.c_str(); }
 
 extern "C" int oi_create(int device, oi_handle** out) {
     if (!out) return fail(OI_ERR_ARG, "oi_create: out is NULL");
-    // The stream groups need their own hardware queues: with the default of 8 connections, streams alias and
-    // serialise (measured +2 % with 32).  Only effective if the CUDA context does not exist yet; never overrides the user.
-    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    // (The stream groups like their own hardware queues: CUDA_DEVICE_MAX_CONNECTIONS=32 in the host's environment before
+    // CUDA initialises is worth +2 %; the library does not touch the environment, see INTEGRATION.md.)
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -100,11 +94,18 @@ extern "C" int oi_create(int device, oi_handle** out) {
     if (p.major != 10)
         return fail(OI_ERR_CUDA, "oi_create: device is sm_" + std::to_string(p.major * 10 + p.minor) +
                                      ", kernels are built for sm_100a only");
+    // opt-in shared-memory sizes are per device context: set them for THIS device (one handle per GPU, several per process)
+    if (int ae = oi_set_kernel_attributes())
+        return fail(OI_ERR_CUDA, std::string("oi_create: cudaFuncSetAttribute: ") + cudaGetErrorString((cudaError_t)ae));
     oi_handle* h = new oi_handle();
     h->device = device;
-    CK(cudaStreamCreate(&h->own_st));
+    cudaError_t ce = cudaStreamCreate(&h->own_st);
+    for (auto& ev : h->ev) if (ce == cudaSuccess) ce = cudaEventCreate(&ev);
+    if (ce != cudaSuccess) {
+        oi_destroy(h);
+        return fail(ce == cudaErrorMemoryAllocation ? OI_ERR_NOMEM : OI_ERR_CUDA, std::string("oi_create: ") + cudaGetErrorString(ce));
+    }
     h->st = h->own_st;
-    for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
     *out = h;
     return OI_OK;
 }
@@ -130,11 +131,9 @@ extern "C" void oi_destroy(oi_handle* h) {
     cudaFree(h->ox); cudaFree(h->oy); cudaFree(h->ot); cudaFree(h->oz);
     free_cells(h);
     cudaFree(h->indices); cudaFree(h->px); cudaFree(h->py); cudaFree(h->pt); cudaFree(h->pr);
-    cudaFree(h->arena); cudaFree(h->d_slots); cudaFree(h->d_slot_phase); cudaFree(h->d_fail); cudaFree(h->d_tickets);
+    cudaFree(h->arena); cudaFree(h->d_slots); cudaFree(h->d_slot_phase); cudaFree(h->d_fail);
     cudaFreeHost(h->h_slots); cudaFreeHost(h->h_slot_phase);
     free_groups(h);
-    cudaFree(h->d_work); cudaFreeHost(h->h_work); cudaFree(h->d_ctl); cudaFree(h->d_pfail); cudaFree(h->d_queue); cudaFree(h->d_acc);
-    cudaFreeHost(h->h_phase_pinned);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->own_st) cudaStreamDestroy(h->own_st);
     delete h;
@@ -176,7 +175,7 @@ extern "C" int oi_set_cells(oi_handle* h, const double* X, int64_t n_cells) {
         CK(cudaMalloc(&h->X, c * 16)); CK(cudaMalloc(&h->counts, c * 4)); CK(cudaMalloc(&h->offsets, (c + 1) * 8));
         CK(cudaMalloc(&h->ca.hyp, c * 40)); CK(cudaMalloc(&h->ca.phase, c * 4)); CK(cudaMalloc(&h->ca.out, c * 64));
         CK(cudaMalloc(&h->ca.nfev, c * 4)); CK(cudaMalloc(&h->ca.status, c * 4)); CK(cudaMalloc(&h->ca.evf, c * 8));
-        CK(cudaMalloc(&h->ca.evg, c * 8 * OI_MAXH)); CK(cudaMalloc(&h->ca.cg, c * sizeof(OiCgState)));
+        CK(cudaMalloc(&h->ca.evg, c * 8 * OI_MAXH)); CK(cudaMalloc(&h->ca.cg, c * OI_OPT_STATE_BYTES));
         h->cell_cap = n_cells;
     }
     h->ca.X = h->X;
@@ -250,7 +249,7 @@ struct OiGroup {
     cudaEvent_t ev[8]{};            // family boundaries of the iteration in flight
     cudaEvent_t done = nullptr;
     OiSlot *d_slots = nullptr, *h_slots = nullptr;
-    int *d_slot_phase = nullptr, *h_slot_phase = nullptr, *d_fail = nullptr, *d_ticket = nullptr;
+    int *d_slot_phase = nullptr, *h_slot_phase = nullptr, *d_fail = nullptr;
     char* arena = nullptr; size_t arena_bytes = 0, used = 0;
     long long tiles = 0;            // sum of N(N+1)/2 over the active cells (work admitted to the group)
     bool high_prio = false;
@@ -279,7 +278,6 @@ static int ensure_batch_buffers(oi_handle* h, size_t want_arena, int want_slots,
         CK(cudaMallocHost(&h->h_slot_phase, (size_t)want_slots * 4));
         h->slot_cap = want_slots;
     }
-    if (!h->d_tickets) CK(cudaMalloc(&h->d_tickets, 16 * 32 * 4));      // one ticket counter per group, 128 B apart
     while ((int)h->groups.size() < G) {
         OiGroup* g = new OiGroup();
         h->groups.push_back(g);                       // owned by the handle from here on (freed in free_groups)
@@ -319,26 +317,15 @@ struct LockstepRun {
     long long cell_tiles(int c) const { long long N = (h->h_counts[c] + OI_NB - 1) / OI_NB; return N * (N + 1) / 2; }
 
     int graph_max_A = 0;            // batches up to this many cells replay a captured graph
-    // k_chol_fused (one launch for all block columns): 0 never, 1 always, 2 only for small batches (<= graph_max_A cells)
-    int fused_chol = 0;
-    bool use_fused(int A, int Nmax) const {
-        return Nmax <= OI_MAX_NB && (fused_chol == 1 || (fused_chol == 2 && A <= graph_max_A));
-    }
 
     // the kernel chain of one lockstep iteration of group g (timed: with the family boundary events)
     int launch_chain(OiGroup& g, int A, int Nmax, const int* cg, cudaStream_t st, bool timed) {
         if (timed) CK(cudaEventRecord(g.ev[0], st));
         oi_launch_build(g.d_slots, A, Nmax, cg, h->ca, pk, st);
         if (timed) CK(cudaEventRecord(g.ev[1], st));
-        if (use_fused(A, Nmax)) {
-            CK(cudaMemsetAsync(g.d_ticket, 0, 4, st));
-            oi_launch_chol_fused(g.d_slots, A, Nmax, cg, g.d_ticket, st);
-            oi_launch_scale_rows(g.d_slots, A, Nmax, cg, st);
-        } else {
-            for (int k = 0; k < Nmax; k++) {
-                oi_launch_chol_update(g.d_slots, A, Nmax, cg, k, st);
-                oi_launch_chol_panel(g.d_slots, A, Nmax, cg, k, st);      // panel of column k + row scaling of row k
-            }
+        for (int k = 0; k < Nmax; k++) {
+            oi_launch_chol_update(g.d_slots, A, Nmax, cg, k, st);
+            oi_launch_chol_panel(g.d_slots, A, Nmax, cg, k, st);      // panel of column k + row scaling of row k
         }
         if (timed) CK(cudaEventRecord(g.ev[2], st));
         oi_launch_fwd(g.d_slots, A, h->ca, pk, t_pred, st);
@@ -394,7 +381,6 @@ struct LockstepRun {
             s.vec = (double*)(g.arena + off); off += align_up((size_t)3 * npad * 8, 256);
             s.part = (double*)(g.arena + off); off += align_up((size_t)(N + 8 + 5 * N * (N + 1) / 2) * 8, 256);
             s.QE = (double*)(g.arena + off); off += align_up((size_t)N * (N + 1) / 2 * 2 * OI_TILE * 8, 256);
-            s.flags = (int*)(g.arena + off); off += align_up((size_t)2 * N * 4, 256);
             s.fail = g.d_fail + a;
             s.pt_off = h->h_offsets[c];
             s.cell = c; s.n = n; s.npad = npad; s.N = N; s.n16 = (n + 15) / 16 * 16; s.pad_ = 0;
@@ -476,8 +462,8 @@ struct LockstepRun {
         S.flops += g.fl; S.flops_factor += g.flf; S.n_evals += g.nev;
         S.flops_chol += g.flf_chol; S.flops_trtri += g.flf_fit / 3; S.flops_lauum += g.flf_fit / 3;
         const bool roww = A >= OI_ROWWISE_MIN_SLOTS_HOST;
-        const int chol_l = use_fused(A, Nmax) ? 1 : 2 * Nmax - 1;
-        const int scale_l = use_fused(A, Nmax) ? (Nmax > 1 ? (roww ? Nmax - 1 : 1) : 0) : (Nmax > 1 ? 1 : 0);   // unfused: 2N launches in all
+        const int chol_l = 2 * Nmax - 1;
+        const int scale_l = Nmax > 1 ? 1 : 0;       // 2N launches per factorisation in all
         S.launches_chol += chol_l + scale_l;
         S.launches_trtri += std::max(0, Nmax - 1); S.launches_lauum += roww ? Nmax : 1;
         S.n_iterations++;
@@ -544,11 +530,11 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
         g.d_slots = h->d_slots + (size_t)gi * per; g.h_slots = h->h_slots + (size_t)gi * per;
         g.d_slot_phase = h->d_slot_phase + (size_t)gi * per; g.h_slot_phase = h->h_slot_phase + (size_t)gi * per;
         g.d_fail = h->d_fail + (size_t)gi * per;
-        g.d_ticket = h->d_tickets + gi * 32;
         g.slot_cap = per; g.active.clear(); g.in_flight = false;
     }
     R.pk = OiPacked{h->px, h->py, h->pt, h->pr};
     // OI_TRACE=<file>: one CSV line per group iteration (active cells, Nmax, stream-ms per kernel family)
+    struct TraceGuard { FILE*& f; ~TraceGuard() { if (f) { std::fclose(f); f = nullptr; } } } trace_guard{R.trace};   // closes on every return path
     if (const char* tp = std::getenv("OI_TRACE")) {
         R.trace = std::fopen(tp, "a");
         if (R.trace) std::fprintf(R.trace, "iter,group,active,Nmax,ms_build,ms_chol,ms_fwd,ms_trtri,ms_alpha,ms_lauum,ms_finalize,flops_factor,t_ms\n");
@@ -561,7 +547,6 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
     if (const char* e = std::getenv("OI_EXPRESS_CAP")) R.express_cap = std::max(std::atoi(e), 1);
     R.iters.assign((size_t)nc, 0);
     R.graph_max_A = 32;
-    if (const char* e = std::getenv("OI_FUSED_CHOL")) R.fused_chol = std::atoi(e);
     if (const char* e = std::getenv("OI_GRAPH_MAX")) R.graph_max_A = std::max(std::atoi(e), 0);
     for (int gi = 0; gi < G; gi++) { OiGroup& g = *h->groups[gi]; g.gcells.clear(); g.last_cells.clear(); g.same_count = 0; }
     // work admitted per bulk group: enough tiles in flight to fill the GPU, few enough that an iteration stays short
@@ -578,17 +563,23 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
             const bool want = R.is_express(gi) && greatest != least;
             if (g.high_prio != want) {               // express lanes run on high-priority streams
                 CK(cudaStreamSynchronize(g.st));
-                CK(cudaStreamDestroy(g.st));
+                cudaStream_t old_st = g.st;
+                g.st = nullptr;                       // never leave a destroyed stream in the group (free_groups skips NULL)
+                CK(cudaStreamDestroy(old_st));
                 CK(cudaStreamCreateWithPriority(&g.st, cudaStreamNonBlocking, want ? greatest : least));
                 g.high_prio = want;
             }
             g.tiles = 0;
         }
     }
-    // fork: the group streams start after everything queued on the handle's stream
-    CK(cudaEventRecord(h->ev[0], h->st));
-    for (int gi = 0; gi < G; gi++) CK(cudaStreamWaitEvent(h->groups[gi]->st, h->ev[0], 0));
+    // fork: the group streams start after everything queued on the handle's stream.  From here on errors do not
+    // return early: they fall through to the join below so that the handle's stream is ordered after every group.
     int rc2 = OI_OK;
+    {
+        cudaError_t fe = cudaEventRecord(h->ev[0], h->st);
+        for (int gi = 0; gi < G && fe == cudaSuccess; gi++) fe = cudaStreamWaitEvent(h->groups[gi]->st, h->ev[0], 0);
+        if (fe != cudaSuccess) rc2 = fail(OI_ERR_CUDA, std::string("run_lockstep: fork: ") + cudaGetErrorString(fe));
+    }
     for (int gi = 0; gi < G && !rc2; gi++) rc2 = R.issue(*h->groups[gi], gi);
     // event loop: poll the groups (non-blocking), express lanes first and again after every serviced bulk group,
     // so that their short iterations are never held up behind the host work of a bulk group
@@ -632,124 +623,7 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
     if (rc2) cudaDeviceSynchronize();
     h->stats.ms_factor += R.ms_factor;
     h->stats.n_groups = G;
-    if (R.trace) std::fclose(R.trace);
     return rc2;
-}
-
-// ------------------------------------------------------------------------------------------
-// the persistent group engine (k_gp_persistent): the host only builds the work list of unfinished
-// cells (largest first), launches the resident grid and reads the phases back; a launch lets every
-// cell advance by up to evals_cap evaluations.  The group size grows when few cells are left so that
-// the optimiser's tail still uses the whole GPU.
-// ------------------------------------------------------------------------------------------
-static int run_persistent(oi_handle* h, std::vector<int>& h_phase, const OiRunConst& rc, double t_pred,
-                          double scratch_gib, int group_size, int evals_cap) {
-    const int nc = (int)h->n_cells;
-    std::vector<int> pending;
-    pending.reserve(nc);
-    for (int c = 0; c < nc; c++)
-        if (h->h_counts[c] > 0 && h_phase[c] != OI_PH_DONE) pending.push_back(c);
-    std::stable_sort(pending.begin(), pending.end(), [&](int a, int b) { return h->h_counts[a] > h->h_counts[b]; });
-    if (pending.empty()) return OI_OK;
-    if (const char* e = std::getenv("OI_GROUP_SIZE")) group_size = std::atoi(e);
-    if (const char* e = std::getenv("OI_EVALS_CAP")) evals_cap = std::atoi(e);
-    if (evals_cap <= 0) evals_cap = 128;
-    if (!h->persist_capacity) h->persist_capacity = oi_persistent_capacity();
-    const int cap = h->persist_capacity;
-    if (cap <= 0) return fail(OI_ERR_CUDA, "run_persistent: the persistent kernel does not fit on this device");
-    if ((int)pending.size() > h->work_cap) {
-        cudaFree(h->d_work); cudaFreeHost(h->h_work);
-        CK(cudaMalloc(&h->d_work, pending.size() * sizeof(OiWork)));
-        CK(cudaMallocHost(&h->h_work, pending.size() * sizeof(OiWork)));
-        h->work_cap = (int)pending.size();
-    }
-    if (cap > h->ctl_cap) {
-        cudaFree(h->d_ctl); cudaFree(h->d_pfail); cudaFree(h->d_queue); cudaFree(h->d_acc);
-        CK(cudaMalloc(&h->d_ctl, (size_t)cap * sizeof(OiGroupCtl))); CK(cudaMalloc(&h->d_pfail, (size_t)cap * 4));
-        CK(cudaMalloc(&h->d_queue, 4)); CK(cudaMalloc(&h->d_acc, sizeof(OiPersistAcc)));
-        h->ctl_cap = cap;
-    }
-    if (nc > h->phase_cap) {
-        cudaFreeHost(h->h_phase_pinned);
-        CK(cudaMallocHost(&h->h_phase_pinned, (size_t)nc * 4));
-        h->phase_cap = nc;
-    }
-    size_t budget;
-    if (scratch_gib > 0) budget = (size_t)(scratch_gib * 1073741824.0);
-    else {
-        size_t fr = 0, tot = 0;
-        CK(cudaMemGetInfo(&fr, &tot));
-        budget = std::min<size_t>((size_t)((fr + h->arena_bytes) * 0.8), (size_t)64 << 30);
-    }
-    FILE* trace = nullptr;
-    if (const char* tp = std::getenv("OI_TRACE")) {
-        trace = std::fopen(tp, "a");
-        if (trace) std::fprintf(trace, "launch,cells,group_size,groups,ms,evals,pred,flops_factor,cyc_build,cyc_chol,cyc_scale,cyc_fwd_trtri,cyc_alpha,cyc_lauum,cyc_final,cyc_idle\n");
-    }
-    OiPacked pk{h->px, h->py, h->pt, h->pr};
-    int rcode = OI_OK;
-    while (!pending.empty()) {
-        const int R = (int)pending.size();
-        int gs = group_size > 0 ? group_size : OI_DEFAULT_GROUP_SIZE;
-        while (gs < 32 && (long long)R * gs * 2 <= cap) gs *= 2;       // few cells left: bigger groups
-        gs = std::max(1, std::min(gs, cap));
-        const size_t stride = align_up(slot_bytes(h->h_counts[pending[0]]), 256);
-        int n_groups = std::min(cap / gs, R);
-        n_groups = (int)std::min<size_t>((size_t)n_groups, std::max<size_t>(budget / stride, 1));
-        if (stride * n_groups > h->arena_bytes) {
-            cudaFree(h->arena); h->arena = nullptr; h->arena_bytes = 0;
-            cudaError_t e = cudaMalloc(&h->arena, stride * n_groups);
-            if (e != cudaSuccess) { rcode = fail(OI_ERR_NOMEM, std::string("run_persistent: scratch: ") + cudaGetErrorString(e)); break; }
-            h->arena_bytes = stride * n_groups;
-        }
-        for (int q = 0; q < R; q++) { int c = pending[q]; h->h_work[q] = OiWork{h->h_offsets[c], c, h->h_counts[c]}; }
-        cudaStream_t st = h->st;
-        CK(cudaMemcpyAsync(h->d_work, h->h_work, (size_t)R * sizeof(OiWork), cudaMemcpyHostToDevice, st));
-        CK(cudaMemsetAsync(h->d_ctl, 0, (size_t)n_groups * sizeof(OiGroupCtl), st));
-        CK(cudaMemsetAsync(h->d_queue, 0, 4, st));
-        CK(cudaMemsetAsync(h->d_acc, 0, sizeof(OiPersistAcc), st));
-        OiPersist P{};
-        P.work = h->d_work; P.n_work = R; P.queue_head = h->d_queue; P.ctl = h->d_ctl; P.scratch = h->arena; P.scratch_stride = stride;
-        P.fail = h->d_pfail; P.gs = gs; P.evals_cap = evals_cap; P.acc = h->d_acc;
-        CK(cudaEventRecord(h->ev[0], st));
-        oi_launch_persistent(P, n_groups, h->ca, pk, rc, t_pred, st);
-        CK(cudaEventRecord(h->ev[1], st));
-        CK(cudaGetLastError());
-        OiPersistAcc acc;
-        CK(cudaMemcpyAsync(h->h_phase_pinned, h->ca.phase, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&acc, h->d_acc, sizeof(acc), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
-        oi_stats& S = h->stats;
-        S.ms_factor += ms; S.ms_persistent += ms;
-        S.flops += acc.flops; S.flops_factor += acc.flops_factor; S.flops_chol += acc.flops_chol;
-        // evaluations contribute n^3/3 to each of chol/trtri/lauum, predictions only to chol
-        S.flops_trtri += (acc.flops_factor - acc.flops_chol) / 2; S.flops_lauum += (acc.flops_factor - acc.flops_chol) / 2;
-        S.n_evals += (int64_t)acc.n_evals; S.n_launches += 1; S.n_iterations += 1; S.launches_persistent += 1;
-        double cyc_tot = 0;
-        for (int q = 0; q < 8; q++) { S.cycles_phase[q] += (double)acc.cycles[q]; cyc_tot += (double)acc.cycles[q]; }
-        if (trace) {
-            std::fprintf(trace, "%lld,%d,%d,%d,%.3f,%llu,%llu,%.6g", (long long)S.launches_persistent, R, gs, n_groups, ms,
-                         acc.n_evals, acc.n_pred, acc.flops_factor);
-            for (int q = 0; q < 8; q++) std::fprintf(trace, ",%.4f", cyc_tot > 0 ? (double)acc.cycles[q] / cyc_tot : 0.0);
-            std::fprintf(trace, "\n");
-        }
-        size_t w = 0;
-        for (int q = 0; q < R; q++) {
-            int c = pending[q];
-            h_phase[c] = h->h_phase_pinned[c];
-            if (h_phase[c] != OI_PH_DONE) pending[w++] = c;
-        }
-        pending.resize(w);
-        S.n_groups = n_groups; S.group_size = gs;
-    }
-    if (trace) std::fclose(trace);
-    return rcode;
-}
-
-static int engine_from_env(int engine) {
-    if (const char* e = std::getenv("OI_ENGINE")) engine = std::atoi(e);
-    return engine == OI_ENGINE_PERSISTENT ? OI_ENGINE_PERSISTENT : OI_ENGINE_LOCKSTEP;
 }
 
 static int pack_points(oi_handle* h, double mean) {
@@ -784,8 +658,7 @@ extern "C" int oi_nlml_grad(oi_handle* h, const double* hypers, int32_t n_hyp, d
     OiRunConst rc{};
     rc.mean = prior_mean; rc.gtol = 1e-5; rc.n_hyp = n_hyp; rc.grad_convention = grad_convention; rc.maxiter = 0;
     reset_stats(h);
-    r = engine_from_env(0) == OI_ENGINE_LOCKSTEP ? run_lockstep(h, phase, rc, 0.0, 0.0, 0, 0)
-                                                    : run_persistent(h, phase, rc, 0.0, 0.0, 0, 0);
+    r = run_lockstep(h, phase, rc, 0.0, 0.0, 0, 0);
     if (r) return r;
     std::vector<double> f(nc), g((size_t)nc * OI_MAXH);
     CK(cudaMemcpy(f.data(), h->ca.evf, (size_t)nc * 8, cudaMemcpyDeviceToHost));
@@ -803,6 +676,9 @@ extern "C" int oi_run(oi_handle* h, const oi_params* p, const double* hypers_in)
     if (p->mode != OI_MODE_FIT && p->mode != OI_MODE_PREDICT) return fail(OI_ERR_ARG, "oi_run: bad mode");
     if (p->mode == OI_MODE_PREDICT && !hypers_in) return fail(OI_ERR_ARG, "oi_run: predict mode needs hypers_in");
     if (p->mode == OI_MODE_FIT && (p->n_hyp < 5 || p->n_hyp > OI_MAXH)) return fail(OI_ERR_ARG, "oi_run: n_hyp must be 5 or 6");
+    if (p->engine != OI_ENGINE_LOCKSTEP)
+        return fail(OI_ERR_ARG, "oi_run: only OI_ENGINE_LOCKSTEP exists (the experimental persistent engine was removed in v1.2)");
+    if (p->optimiser != OI_OPT_CG && p->optimiser != OI_OPT_LBFGS) return fail(OI_ERR_ARG, "oi_run: bad optimiser");
     if (!h->have_nbr) return fail(OI_ERR_STATE, "oi_run: call oi_gather_neighbours first");
     CK(cudaSetDevice(h->device));
     const int nc = (int)h->n_cells;
@@ -813,6 +689,7 @@ extern "C" int oi_run(oi_handle* h, const oi_params* p, const double* hypers_in)
     OiRunConst rc{};
     rc.mean = p->prior_mean; rc.gtol = p->gtol > 0 ? p->gtol : 1e-5; rc.n_hyp = p->mode == OI_MODE_FIT ? p->n_hyp : 5;
     rc.grad_convention = p->grad_convention; rc.maxiter = p->maxiter;
+    rc.optimiser = p->optimiser == OI_OPT_LBFGS ? 1 : 0;
     for (int q = 0; q < OI_MAXH; q++) rc.x0[q] = p->x0[q];
     std::vector<int> phase(nc);
     // cells without observations: NaN tuple, status NO_OBS (the reference would raise inside pdist)
@@ -834,9 +711,7 @@ extern "C" int oi_run(oi_handle* h, const oi_params* p, const double* hypers_in)
         CK(cudaMemcpyAsync(h->ca.hyp, hypers_in, (size_t)nc * 40, cudaMemcpyHostToDevice, h->st));
     }
     CK(cudaStreamSynchronize(h->st));   // staging vectors go out of scope below
-    r = engine_from_env(p->engine) == OI_ENGINE_LOCKSTEP
-            ? run_lockstep(h, phase, rc, p->t_pred, p->scratch_gib, p->max_active, p->n_groups)
-            : run_persistent(h, phase, rc, p->t_pred, p->scratch_gib, p->group_size, p->evals_per_launch);
+    r = run_lockstep(h, phase, rc, p->t_pred, p->scratch_gib, p->max_active, p->n_groups);
     if (r) return r;
     CK(cudaEventRecord(h->ev[9], h->st));
     CK(cudaStreamSynchronize(h->st));

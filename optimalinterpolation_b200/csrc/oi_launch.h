@@ -6,7 +6,6 @@
 #define OI_THREADS 128                 // threads of every tile CTA (4 warps, 2x2 warp tiles of 32x32)
 #define OI_ROWWISE_MIN_SLOTS_HOST 96   // batches at least this big launch the tile-parallel kernels one block row at a time
 #define OI_DEFAULT_GROUPS 8
-#define OI_DEFAULT_GROUP_SIZE 4        // CTAs per group of the persistent engine while cells are plentiful
 #define OI_SMEM_BYTES (2 * OI_NB * 68 * 8 + 4 * 64 * 8 + 16)   // T + W of the diagonal factor + per-warp scratch + flag (>= the cp.async pipeline)
 #ifndef STAGES
 #define STAGES 3
@@ -15,7 +14,7 @@
 
 struct OiRunConst {
     double mean, gtol;
-    int n_hyp, grad_convention, maxiter;
+    int n_hyp, grad_convention, maxiter, optimiser;
     double x0[6];
 };
 void oi_launch_count(const double* ox, const double* oy, const double* ot, int n_obs, const double* X, int n_cells, double r2,
@@ -27,7 +26,6 @@ void oi_launch_pack(const int* indices, long long total, const double* ox, const
                     const double* oz, double mean, double t_shift, double* px, double* py, double* pt, double* pr, cudaStream_t st);
 void oi_launch_build(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, OiCellArrays ca, OiPacked pk, cudaStream_t st);
 void oi_launch_chol_update(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int k, cudaStream_t st);
-void oi_launch_chol_fused(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int* ticket, cudaStream_t st);
 void oi_launch_chol_panel(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int k, cudaStream_t st);
 void oi_launch_scale_rows(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, cudaStream_t st);
 void oi_launch_fwd(const OiSlot* slots, int A, OiCellArrays ca, OiPacked pk, double t_pred, cudaStream_t st);
@@ -35,7 +33,6 @@ void oi_launch_trtri(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, in
 void oi_launch_alpha(const OiSlot* slots, int A, int Nmax, const int* phase, cudaStream_t st);
 void oi_launch_lauum_trace(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, OiCellArrays ca, OiPacked pk, cudaStream_t st);
 
-void oi_launch_persistent(const OiPersist& P, int n_groups, OiCellArrays ca, OiPacked pk, OiRunConst rc, double t_pred, cudaStream_t st);
-int oi_persistent_capacity();   // co-resident CTAs of the persistent kernel on the current device
+int oi_set_kernel_attributes();   // > 48 KB dynamic shared memory opt-in for the CURRENT device; returns a cudaError_t
 void oi_launch_cg_init(OiCellArrays ca, int n_cells, OiRunConst rc, cudaStream_t st);
 void oi_launch_finalize(const OiSlot* slots, int A, OiCellArrays ca, OiRunConst rc, int* slot_phase, cudaStream_t st);

@@ -11,16 +11,24 @@
 #include "oi_types.h"
 #include "oi_launch.h"
 #include "cg_scipy.h"
+#include "lbfgs_fast.h"
 
 #define LOG_2PI 1.8378770664093453   // np.log(2*np.pi)
 
 __global__ void k_cg_init(OiCellArrays ca, int n_cells, OiRunConst rc) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cells) return;
-    OiCgState* S = (OiCgState*)ca.cg + c;
+    double dummy[OI_MAXH] = {0, 0, 0, 0, 0, 0};
+    if (rc.optimiser == 1) {
+        OiLbfgsState* S = (OiLbfgsState*)((char*)ca.cg + (size_t)c * OI_OPT_STATE_BYTES);
+        oi_lbfgs_init(*S, rc.x0, rc.n_hyp, rc.maxiter, rc.gtol);
+        oi_lbfgs_resume(*S, 0.0, dummy);
+        for (int q = 0; q < 5; q++) ca.hyp[5 * (size_t)c + q] = exp(S->req_x[q]);
+        return;
+    }
+    OiCgState* S = (OiCgState*)((char*)ca.cg + (size_t)c * OI_OPT_STATE_BYTES);
     OiCgState L;
     oi_cg_init(L, rc.x0, rc.n_hyp, rc.maxiter, rc.gtol);
-    double dummy[OI_MAXH] = {0, 0, 0, 0, 0, 0};
     oi_cg_resume(L, 0.0, dummy);          // first resume only publishes x0 as the first request
     *S = L;
     for (int q = 0; q < 5; q++) ca.hyp[5 * (size_t)c + q] = exp(L.req_x[q]);
@@ -73,8 +81,21 @@ __device__ __noinline__ int warp_finalize(const OiSlot s, const OiCellArrays ca,
         if (phase == OI_PH_EVAL) {
             ca.evf[s.cell] = f;
             for (int q = 0; q < OI_MAXH; q++) ca.evg[OI_MAXH * (size_t)s.cell + q] = g[q];
+        } else if (rc.optimiser == 1) {
+            // fast mode: exact-gradient L-BFGS (lbfgs_fast.h); the state stays in global memory (1.2 KB per cell)
+            OiLbfgsState* Sg = (OiLbfgsState*)((char*)ca.cg + (size_t)s.cell * OI_OPT_STATE_BYTES);
+            int r = oi_lbfgs_resume(*Sg, f, g);
+            if (r == OI_CG_NEED_EVAL) {
+                for (int q = 0; q < 5; q++) h[q] = exp(Sg->req_x[q]);
+                newphase = OI_PH_FIT;
+            } else {
+                for (int q = 0; q < 5; q++) h[q] = exp(Sg->xk[q]);
+                ca.nfev[s.cell] = Sg->nfev;
+                ca.status[s.cell] = Sg->status == 3 ? 5 : Sg->status;
+                newphase = OI_PH_PREDICT;
+            }
         } else {
-            OiCgState* Sg = (OiCgState*)ca.cg + s.cell;
+            OiCgState* Sg = (OiCgState*)((char*)ca.cg + (size_t)s.cell * OI_OPT_STATE_BYTES);
             OiCgState L = *Sg;
             int r = oi_cg_resume(L, f, g);
             *Sg = L;

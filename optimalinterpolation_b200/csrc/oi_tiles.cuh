@@ -81,10 +81,7 @@ __device__ __forceinline__ double pair_Q(double dx, double dy, double dt) {
 __device__ __forceinline__ void tile_build(const OiSlot& s, const OiCellArrays& ca, const OiPacked& pk, int i, int j, bool want_qe,
                                            double* smem) {
     const int tid = threadIdx.x;
-    if (i == 0) {
-        if (tid == 0) *s.fail = 0;
-        for (int q = tid; q < 2 * s.N; q += OI_THREADS) s.flags[q] = 0;      // dependency flags of k_chol_fused
-    }
+    if (i == 0 && tid == 0) *s.fail = 0;
     double(*ru)[NB] = (double(*)[NB])smem;
     double(*cu)[NB] = ru + 3;
     const double* h = ca.hyp + 5 * (size_t)s.cell;
@@ -382,18 +379,18 @@ __device__ __forceinline__ void diag_factor_invert(double* P, double* sc, int* s
 __device__ __forceinline__ void tile_chol_update(const OiSlot& s, int i, int k, double* smem) {
     const long long ld = s.npad;
     double acc[4][4][2];
-    ACC_ZERO(acc);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 1, wn = warp & 1;
-    // the tile being updated is fetched up front so its latency hides behind the K loop
-    double2 cin[4][4];
-    {
-        const double* Cr = s.M + (long long)i * NB * ld + (long long)k * NB;
+    double* Cg = s.M + (long long)i * NB * ld + (long long)k * NB;
+    // The accumulators start at -A_ik (the DMMA fragment layout is the tile's own row/col layout), so the K loop leaves
+    // -(A_ik - sum L_ij L_kj^T) in them: no second copy of the tile in registers (it cost 64 registers and spills at
+    // 4 CTAs/SM), and the loads overlap the pipeline prologue.
 #pragma unroll
-        for (int mb = 0; mb < 4; mb++)
+    for (int mb = 0; mb < 4; mb++)
 #pragma unroll
-            for (int nb = 0; nb < 4; nb++)
-                cin[mb][nb] = __ldcg((const double2*)&Cr[(long long)FRAG_ROW(wm, mb, lane) * ld + FRAG_COL(wn, nb, lane)]);
-    }
+        for (int nb = 0; nb < 4; nb++) {
+            const double2 c = __ldcg((const double2*)&Cg[(long long)FRAG_ROW(wm, mb, lane) * ld + FRAG_COL(wn, nb, lane)]);
+            acc[mb][nb][0] = -c.x; acc[mb][nb][1] = -c.y;
+        }
     {
         // rows of block i / cols of block k beyond the cell's size are padding; of the diagonal tile only
         // the lower triangle is needed (the warp above the diagonal idles)
@@ -402,19 +399,18 @@ __device__ __forceinline__ void tile_chol_update(const OiSlot& s, int i, int k, 
         gemm_nt_stream(acc, s.M + (long long)i * NB * ld, ld, s.M + (long long)k * NB * ld, ld, 0, k * NB, smem,
                        [sr](int) { return sr; });
     }
-    double* Cg = s.M + (long long)i * NB * ld + (long long)k * NB;
     if (i != k) {
 #pragma unroll
         for (int mb = 0; mb < 4; mb++)
 #pragma unroll
             for (int nb = 0; nb < 4; nb++) {
-                double2 v = cin[mb][nb];
-                v.x -= acc[mb][nb][0]; v.y -= acc[mb][nb][1];
+                double2 v;
+                v.x = -acc[mb][nb][0]; v.y = -acc[mb][nb][1];
                 *(double2*)&Cg[(long long)FRAG_ROW(wm, mb, lane) * ld + FRAG_COL(wn, nb, lane)] = v;
             }
         return;
     }
-    // ---- diagonal tile: P = A_kk - acc, factor + invert in shared memory (packed L / W layout, see above) ----
+    // ---- diagonal tile: P = A_kk - sum = -acc, factor + invert in shared memory (packed L / W layout, see above) ----
     double* P = smem;                          // [64][TS]
     double* sc = smem + NB * TS + warp * 64;   // per-warp 8x8 scratch
     int* s_bad = (int*)(smem + NB * TS + 4 * 64);
@@ -423,8 +419,8 @@ __device__ __forceinline__ void tile_chol_update(const OiSlot& s, int i, int k, 
 #pragma unroll
         for (int nb = 0; nb < 4; nb++) {
             int r = FRAG_ROW(wm, mb, lane), c = FRAG_COL(wn, nb, lane);
-            P[r * TS + c] = cin[mb][nb].x - acc[mb][nb][0];
-            P[r * TS + c + 1] = cin[mb][nb].y - acc[mb][nb][1];
+            P[r * TS + c] = -acc[mb][nb][0];
+            P[r * TS + c + 1] = -acc[mb][nb][1];
         }
     if (tid == 0) *s_bad = 0;
     __syncthreads();

@@ -18,7 +18,6 @@ struct OiSlot {
     double* QE;       // per lower tile (i,j): 64x64 Q = scaled distances, then 64x64 E = exp(-Q), written by the covariance
                       // build and re-read by the trace epilogue (trades FP64-pipe work, shared with DMMA, for idle HBM bandwidth)
     int* fail;        // set when a Cholesky pivot is <= 0 or NaN (np.linalg.LinAlgError in the reference)
-    int* flags;       // [2N] dependency flags of the fused Cholesky: diag_done[k] | col_done[k] (finished off-diagonal tiles)
     long long pt_off; // offset of this cell's points in the packed (CSR-ordered) coordinate arrays
     int cell, n, npad, N;
     int n16, pad_;    // n rounded up to the DMMA K chunk (16): K loops and edge sub-tiles stop here
@@ -39,27 +38,3 @@ struct OiCellArrays {
 struct OiPacked {
     const double* x; const double* y; const double* t; const double* r;   // r = z - prior mean
 };
-
-// ---- persistent group engine (oi_kernels.cu: k_gp_persistent) ----
-struct OiWork { long long pt_off; int cell, n; };            // one unfinished cell of the work list (sorted by descending n)
-struct OiGroupCtl { unsigned count; int cur[2]; int pad_[29]; };   // 128 B per group: barrier counter + current work index
-struct OiPersistAcc {
-    unsigned long long cycles[8];      // CTA clock cycles per phase (build, chol, scale, fwd+trtri, alpha, lauum, finalize, idle)
-    double flops, flops_factor, flops_chol;
-    unsigned long long n_evals, n_pred;
-};
-struct OiPersist {
-    const OiWork* work; int n_work;
-    int* queue_head;                   // next work index
-    OiGroupCtl* ctl;                   // [n_groups]
-    char* scratch; size_t scratch_stride;   // per-group scratch (sized for the largest cell of the work list)
-    int* fail;                         // [n_groups]
-    int gs;                            // CTAs per group
-    int evals_cap;                     // evaluations a group spends on one cell before it takes the next
-    OiPersistAcc* acc;
-};
-
-// ---- fused Cholesky (oi_kernels.cu: k_chol_fused): CTA tickets are laid out column by column,
-// segment 2k = diagonal tiles (k,k) of all cells with N > k, segment 2k+1 = off-diagonal tiles of column k
-#define OI_MAX_NB 128
-struct OiCholPlan { int Nmax; int off[2 * OI_MAX_NB + 1]; };

@@ -105,7 +105,7 @@ class Handle:
 
     def make_params(self, radius_m, t_pred, prior_mean, x0=None, mode=0, grad_convention=0, maxiter=0,
                     gtol=0.0, scratch_gib=0.0, max_active=0, n_groups=0, engine=0, group_size=0,
-                    evals_per_launch=0):
+                    evals_per_launch=0, optimiser=0):
         p = _lib.OiParams()
         p.radius_m, p.t_pred, p.prior_mean = float(radius_m), float(t_pred), float(prior_mean)
         x0 = [0.0] * 5 if x0 is None else list(x0)
@@ -115,6 +115,7 @@ class Handle:
         p.mode, p.grad_convention, p.maxiter = int(mode), int(grad_convention), int(maxiter)
         p.gtol, p.scratch_gib, p.max_active = float(gtol), float(scratch_gib), int(max_active)
         p.n_groups, p.engine, p.group_size, p.evals_per_launch = int(n_groups), int(engine), int(group_size), int(evals_per_launch)
+        p.optimiser = int(optimiser)     # 0 = scipy-CG restatement (parity mode), 1 = exact-gradient L-BFGS (fast mode)
         return p
 
     def run(self, params, hypers_in=None):

@@ -115,3 +115,11 @@ def make_small_day(seed: int = 7, n_side: int = 40, ice_radius_cells: float = 14
                     centre=(n_side // 2, n_side // 2), radius_km=radius_km,
                     tracks_per_day=tracks_per_day, seed=seed,
                     s3_hole_cells=4.0, cs2_hole_cells=1.0)
+
+
+def make_day_cfg5(seed: int = 20190128, tracks_per_day: int = 17) -> SyntheticDay:
+    """BASELINE.json configs[4]: the 12.5 km lattice with a 500 km search radius (the reference's knobs
+    ``grid_res = 12.5`` at GPR_CS2S3.py:201 with 640x640 product grids, ``radius = 500`` at :208); same ice disc, holes
+    and track geometry as ``make_day`` in kilometres.  ~76k ice cells, ~60k observations, n per cell ~1500...5100."""
+    return make_day(n_side=640, grid_res_km=12.5, ice_radius_cells=156.0, centre=(274, 274), radius_km=500.0,
+                    tracks_per_day=tracks_per_day, seed=seed, s3_hole_cells=76.0, cs2_hole_cells=18.0)

@@ -1,6 +1,7 @@
 // Host build of the optimiser state machine (optimalinterpolation_b200/csrc/cg_scipy.h) for CPU tests:
 // tests drive it with a Python objective and compare against scipy.optimize.minimize(method='CG').
 #include "../optimalinterpolation_b200/csrc/cg_scipy.h"
+#include "../optimalinterpolation_b200/csrc/lbfgs_fast.h"
 #include <cstdlib>
 extern "C" {
 OiCgState* cgh_new() { return (OiCgState*)calloc(1, sizeof(OiCgState)); }
@@ -13,4 +14,26 @@ double cgh_fval(OiCgState* s) { return s->old_fval; }
 int cgh_status(OiCgState* s) { return s->status; }
 int cgh_nit(OiCgState* s) { return s->k; }
 int cgh_nfev(OiCgState* s) { return s->nfev; }
+// fast-mode optimiser (lbfgs_fast.h)
+OiLbfgsState* lbh_new() { return (OiLbfgsState*)calloc(1, sizeof(OiLbfgsState)); }
+void lbh_free(OiLbfgsState* s) { free(s); }
+void lbh_init(OiLbfgsState* s, const double* x0, int dim, int maxiter, double pgtol) { oi_lbfgs_init(*s, x0, dim, maxiter, pgtol); }
+int lbh_resume(OiLbfgsState* s, double f, const double* g) { return oi_lbfgs_resume(*s, f, g); }
+const double* lbh_req_x(OiLbfgsState* s) { return s->req_x; }
+const double* lbh_x(OiLbfgsState* s) { return s->xk; }
+double lbh_fval(OiLbfgsState* s) { return s->fk; }
+int lbh_status(OiLbfgsState* s) { return s->status; }
+int lbh_nit(OiLbfgsState* s) { return s->k; }
+int lbh_nfev(OiLbfgsState* s) { return s->nfev; }
+}
+// unit access to the interpolation helpers (rounding checks against scipy's Python, tests/test_cg.py)
+extern "C" {
+int cgh_cubicmin(double a, double fa, double fpa, double b, double fb, double c, double fc, double* x) { return oicg::cubicmin(a, fa, fpa, b, fb, c, fc, *x) ? 1 : 0; }
+int cgh_quadmin(double a, double fa, double fpa, double b, double fb, double* x) { return oicg::quadmin(a, fa, fpa, b, fb, *x) ? 1 : 0; }
+}
+extern "C" double cgh_fma(double a, double b, double c) { return fma(a, b, c); }
+extern "C" double cgh_cube(double x) { return oicg::cube(x); }
+extern "C" void cgh_dcstep(double* v, int* brackt, double fp, double dp, double stpmin, double stpmax) {
+    // v = {stx, fx, dx, sty, fy, dy, stp}
+    oicg::dcstep(v[0], v[1], v[2], v[3], v[4], v[5], v[6], fp, dp, *brackt, stpmin, stpmax);
 }

@@ -1,6 +1,8 @@
 import os
 import sys
 
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")   # the oracle's cells are small; BLAS threads only fight each other
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

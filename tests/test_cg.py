@@ -58,3 +58,45 @@ def test_smlii_trace_identical(small_day, small_oracle, cell):
     _, inp, out, _ = small_oracle.cell_data(cell)
     mX = np.ones(len(out)) * small_day.mean
     _compare(lambda x: nlml_grad(x, inp, out, mX), small_day.x0)
+
+
+def test_interpolation_helpers_round_like_scipy():
+    """_cubicmin / _quadmin / dcstep on 20000 random argument sets: the restatement must round like scipy's Python except
+    where scipy's `x**2` / `x**3` (libm pow on numpy scalars, not reproducible on the device) is one ulp off the correctly
+    rounded power -- measured 0.16 % of the cubic calls, 0 % of the quadratic ones, 0.001 % of dcstep.  (Round 1 accumulated
+    the 2x2 np.dot of _cubicmin in the other order: 27 % of the calls differed by an ulp, which no optimiser trace of this
+    file's other tests happened to exercise.)"""
+    import ctypes
+    import cg_driver
+    from scipy.optimize._linesearch import _cubicmin, _quadmin
+    from scipy.optimize._dcsrch import dcstep
+    L = cg_driver._lib()
+    L.cgh_cubicmin.argtypes = [ctypes.c_double] * 7 + [ctypes.POINTER(ctypes.c_double)]
+    L.cgh_quadmin.argtypes = [ctypes.c_double] * 5 + [ctypes.POINTER(ctypes.c_double)]
+    L.cgh_dcstep.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_double] * 4
+    rng = np.random.default_rng(0)
+    x = ctypes.c_double()
+    f64 = np.float64
+    bad = {"cubic": 0, "quad": 0, "dcstep": 0}
+    N = 20000
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(N):
+            a = f64(rng.uniform(0, 1e-3)); b = f64(a + rng.uniform(1e-6, 1e-2)); c = f64(a + rng.uniform(1e-6, 1e-2))
+            fa = f64(-230 + rng.normal()); fpa = f64(-abs(rng.normal()) * 10 ** rng.uniform(-3, 3))
+            fb = f64(fa + rng.normal() * 10 ** rng.uniform(-6, 1)); fc = f64(fa + rng.normal() * 10 ** rng.uniform(-6, 1))
+            r = _cubicmin(a, fa, fpa, b, fb, c, fc)
+            ok = L.cgh_cubicmin(a, fa, fpa, b, fb, c, fc, ctypes.byref(x))
+            bad["cubic"] += (r is None) != (ok == 0) or (r is not None and float(r) != x.value)
+            r = _quadmin(a, fa, fpa, b, fb)
+            ok = L.cgh_quadmin(a, fa, fpa, b, fb, ctypes.byref(x))
+            bad["quad"] += (r is None) != (ok == 0) or (r is not None and float(r) != x.value)
+            stx = rng.uniform(0, 1); sty = stx + rng.normal() * 0.5; stp = stx + rng.normal() * 0.5
+            fx = rng.normal(); fy = fx + abs(rng.normal()); fp = fx + rng.normal()
+            dx = -abs(rng.normal()); dy = rng.normal(); dp = rng.normal()
+            br = bool(rng.integers(0, 2)); lo = min(stx, sty) if br else 0.0; hi = max(stx, sty) if br else stp * 5 + 1
+            r = dcstep(stx, fx, dx, sty, fy, dy, stp, fp, dp, br, lo, hi)
+            v = np.array([stx, fx, dx, sty, fy, dy, stp]); bb = ctypes.c_int(int(br))
+            L.cgh_dcstep(v.ctypes.data, ctypes.byref(bb), fp, dp, lo, hi)
+            bad["dcstep"] += not (np.array_equal(np.array([float(q) for q in r[:7]]), v, equal_nan=True) and bool(r[7]) == bool(bb.value))
+    assert bad["quad"] == 0 and bad["cubic"] <= 0.005 * N and bad["dcstep"] <= 0.001 * N, bad

@@ -180,10 +180,10 @@ def test_fit_matches_oracle(small_day, small_oracle):
     assert np.mean(ok_nl) >= 0.90
 
 
-def test_engines_and_groupings_bit_identical(small_day):
-    """The lockstep engine with 1 or 8 stream groups and tiny batches, and the persistent group engine with
-    group sizes 1, 3 and 8, all run the same tile code: fitted outputs, nfev and status must be bit-identical
-    (=> results do not depend on batch composition, scheduling or GPU count)."""
+def test_groupings_bit_identical(small_day):
+    """1 or 8 stream groups, tiny batches, forced express-lane hand-over, with and without CUDA-graph replay: fitted
+    outputs, nfev and status must be bit-identical (=> results do not depend on batch composition, scheduling or GPU
+    count).  (The experimental persistent engine and the flag-based fused Cholesky of round 1 were removed.)"""
     import optimalinterpolation_b200 as oi
     d = small_day
     cells = np.linspace(0, len(d.X) - 1, 30).round().astype(int)
@@ -191,13 +191,10 @@ def test_engines_and_groupings_bit_identical(small_day):
     h.set_observations(d.x_train, d.y_train, d.t_train, d.z); h.set_cells(d.X[cells]); h.gather_neighbours(d.radius_km * 1000.0)
     import os
     ref = None
-    for kw in (dict(engine=0, n_groups=1), dict(engine=0, n_groups=8), dict(engine=0, n_groups=3, max_active=7),
-               dict(engine=0, n_groups=4, express=(2, 5, 3)), dict(engine=0, n_groups=2, nograph=True), dict(engine=0, n_groups=2, fused=True),
-               dict(engine=1, group_size=1), dict(engine=1, group_size=3, evals_per_launch=5), dict(engine=1, group_size=8)):
+    for kw in (dict(n_groups=1), dict(n_groups=8), dict(n_groups=3, max_active=7),
+               dict(n_groups=4, express=(2, 5, 3)), dict(n_groups=2, nograph=True)):
         kw = dict(kw)
         ex = kw.pop("express", None)
-        if kw.pop("fused", False):       # single-launch fused Cholesky (ticketed dependency flags) instead of 2 launches per column
-            os.environ["OI_FUSED_CHOL"] = "1"
         if kw.pop("nograph", False):     # the first configurations replay CUDA graphs (batches <= 32 cells); this one does not
             os.environ["OI_GRAPH_MAX"] = "0"
         if ex:   # force the express-lane hand-over (lanes, after-iterations, lane capacity) on this tiny problem
@@ -205,7 +202,7 @@ def test_engines_and_groupings_bit_identical(small_day):
         try:
             h.run(h.make_params(d.radius_km * 1000.0, d.T_mid, d.mean, d.x0, mode=0, **kw))
         finally:
-            for k in ("OI_EXPRESS", "OI_EXPRESS_AFTER", "OI_EXPRESS_CAP", "OI_GRAPH_MAX", "OI_FUSED_CHOL"):
+            for k in ("OI_EXPRESS", "OI_EXPRESS_AFTER", "OI_EXPRESS_CAP", "OI_GRAPH_MAX"):
                 os.environ.pop(k, None)
         if ex:
             assert h.stats()["n_express_cells"] > 0
@@ -218,6 +215,9 @@ def test_engines_and_groupings_bit_identical(small_day):
         else:
             assert np.array_equal(r["out"], ref["out"], equal_nan=True), kw
             assert np.array_equal(r["nfev"], ref["nfev"]) and np.array_equal(r["status"], ref["status"]), kw
+    # the removed engine is refused, not silently replaced
+    with pytest.raises(oi.gpr.OIError):
+        h.run(h.make_params(d.radius_km * 1000.0, d.T_mid, d.mean, d.x0, mode=0, engine=1))
     h.close()
 
 
