@@ -17,7 +17,11 @@ def test_reference_arm_json_line():
     assert d["impl"] == "reference" and d["unit"] == "cells/s" and d["higher_is_better"] is True
     assert d["metric"].startswith("GP cells/sec") and d["value"] > 0 and d["n_gpus"] == 1
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "SMLII" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "whole GPR3D fits" in cb["sample"]
+    # measured, not modelled: ms_per_step is consistent with value, and the sampling wall time is reported separately
+    assert abs(d["ms_per_step"] - d["config"]["cells_per_step"] / d["value"] * 1e3) < 1e-6 * d["ms_per_step"]
+    assert d["sample_wall_ms_per_step"] > 0
+    assert d["config"]["workload"].startswith("2/16 stripes of the synthetic 25 km pan-Arctic day")
     assert d["e2e"] == {"value": d["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
