@@ -19,7 +19,8 @@ After the loop, while the wall-clock budget (--budget-s, default 520 s from proc
 the CPU baseline sample, a single-stream pass that times each kernel family, and the WHOLE day in one call
 (BASELINE.json configs[1]; ~8 steps' worth, reported under "full_day").
 
-  --workload cfg5  : BASELINE.json configs[4] (12.5 km lattice, 500 km radius, n ~ 1200...5400), 32 cells per GPU and step
+  --workload cfg5  : BASELINE.json configs[4] (12.5 km lattice, 500 km radius, n ~ 1200...5400), 64 cells per GPU and step
+  --workload realmask : the same tracks over the real ice mask of a QuickLook day (17 697 cells, n 2...2326)
   --impl reference : the reference's CPU path (oracle port, see oracle/) on the host cores, whole fits, time-boxed
 """
 import argparse
@@ -40,7 +41,7 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before CUDA initi
 
 METRIC = "GP cells/sec (fit+predict), 25km Arctic day"
 N_STRIPES = 16
-CFG5_CELLS_PER_GPU = 32
+CFG5_CELLS_PER_GPU = 64
 
 
 def parse():
@@ -49,7 +50,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="day25", choices=["day25", "cfg5"])
+    ap.add_argument("--workload", default="day25", choices=["day25", "cfg5", "realmask"])
     ap.add_argument("--optimiser", default="cg", choices=["cg", "lbfgs"],
                     help="cg = the reference's scipy-CG restatement (parity mode, the headline); lbfgs = exact-gradient L-BFGS fast mode")
     ap.add_argument("--stripes-per-gpu", type=int, default=2)
@@ -94,8 +95,12 @@ class ClockSampler(threading.Thread):
 
 def make_workload(args, world):
     """The synthetic day and the cell indices of one step (deterministic; both arms use it)."""
-    from optimalinterpolation_b200.synthetic import make_day, make_day_cfg5
-    if args.workload == "cfg5":
+    from optimalinterpolation_b200.synthetic import make_day, make_day_cfg5, make_day_real_mask
+    if args.workload == "realmask":
+        day = make_day_real_mask(os.path.join(ROOT, "tests", "golden", "quicklook_icemask.npz"))
+        nc = len(day.X)
+        cells = np.sort(np.concatenate([np.arange(s, nc, N_STRIPES) for s in range(min(world * args.stripes_per_gpu, N_STRIPES))]))
+    elif args.workload == "cfg5":
         day = make_day_cfg5()
         cells = np.unique(np.linspace(0, len(day.X) - 1, CFG5_CELLS_PER_GPU * world).round().astype(np.int64))
     else:
@@ -112,6 +117,9 @@ def make_config(args, world, day, cells, counts_step):
     if args.workload == "cfg5":
         wl = (f"{len(cells)} cells ({CFG5_CELLS_PER_GPU} per GPU) of the synthetic 12.5 km / 500 km day (BASELINE.json configs[4]: 640x640 "
               f"lattice, {len(day.X)} ice cells, {day.z.size} obs, 9 days)")
+    elif args.workload == "realmask":
+        wl = (f"{world * args.stripes_per_gpu}/16 stripes of the synthetic 25 km day over the REAL ice mask of the reference's QuickLook product "
+              f"of 2019-01-28 (SURVEY.md 8d option B: {len(day.X)} ice cells, {day.z.size} obs, r=300 km, 9 days)")
     else:
         wl = (f"{world * args.stripes_per_gpu}/16 stripes of the synthetic 25 km pan-Arctic day "
               f"(SURVEY.md 8d: 320x320 lattice, {len(day.X)} ice cells, {day.z.size} obs, r=300 km, 9 days)")

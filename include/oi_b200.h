@@ -142,6 +142,10 @@ int oi_run(oi_handle* h, const oi_params* p, const double* hypers_in);
 /* out[n_cells][8]; nfev_out/status_out/n_out[n_cells] may be NULL. */
 int oi_get_results(oi_handle* h, double* out, int32_t* n_out, int32_t* nfev_out, int32_t* status_out);
 int oi_get_stats(oi_handle* h, oi_stats* s);
+/* Diagnostic (tools/cg_diagnose.py): record every objective evaluation the optimiser of ONE cell sees during the next
+ * OI_MODE_FIT runs -- rows of 12 doubles: natural-unit hyperparameters (5), value, gradient (6).  cell < 0: off. */
+int oi_debug_trace(oi_handle* h, int64_t cell, int32_t capacity);
+int oi_get_debug_trace(oi_handle* h, double* rows, int32_t* n_rows);
 
 /* The whole day in one call: set_observations + set_cells + gather + run + get_results. */
 int oi_gpr_day(oi_handle* h, const double* x, const double* y, const double* t, const double* z, int64_t n_obs,

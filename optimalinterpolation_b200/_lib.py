@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "liboi_b200.so")
 
 EXPORTS = ("oi_version", "oi_last_error", "oi_create", "oi_destroy", "oi_set_observations", "oi_set_cells",
            "oi_gather_neighbours", "oi_get_neighbours", "oi_nlml_grad", "oi_run", "oi_get_results",
-           "oi_get_stats", "oi_gpr_day", "oi_set_stream", "oi_sizeof_params", "oi_sizeof_stats", "oi_set_time_window")
+           "oi_get_stats", "oi_gpr_day", "oi_set_stream", "oi_sizeof_params", "oi_sizeof_stats", "oi_set_time_window", "oi_debug_trace", "oi_get_debug_trace")
 
 
 class OiParams(C.Structure):
@@ -74,6 +74,8 @@ def load():
     L.oi_get_results.argtypes = [vp, dp, ip, ip, ip]
     L.oi_get_stats.argtypes = [vp, C.POINTER(OiStats)]
     L.oi_gpr_day.argtypes = [vp, dp, dp, dp, dp, C.c_int64, dp, C.c_int64, C.POINTER(OiParams), dp, dp, ip, ip, ip]
+    L.oi_debug_trace.argtypes = [vp, C.c_int64, C.c_int32]
+    L.oi_get_debug_trace.argtypes = [vp, dp, ip]
     L.oi_sizeof_params.restype = C.c_int
     L.oi_sizeof_stats.restype = C.c_int
     if L.oi_sizeof_params() != C.sizeof(OiParams) or L.oi_sizeof_stats() != C.sizeof(OiStats):

@@ -57,6 +57,7 @@ struct oi_handle {
     std::vector<struct OiGroup*> groups;
     oi_stats stats{};
     bool have_results = false;
+    double* d_dbg = nullptr; int* d_dbg_count = nullptr; int dbg_cell = -1, dbg_cap = 0;
 };
 
 struct OiGroup;
@@ -131,6 +132,7 @@ extern "C" void oi_destroy(oi_handle* h) {
     cudaFree(h->ox); cudaFree(h->oy); cudaFree(h->ot); cudaFree(h->oz);
     free_cells(h);
     cudaFree(h->indices); cudaFree(h->px); cudaFree(h->py); cudaFree(h->pt); cudaFree(h->pr);
+    cudaFree(h->d_dbg); cudaFree(h->d_dbg_count);
     cudaFree(h->arena); cudaFree(h->d_slots); cudaFree(h->d_slot_phase); cudaFree(h->d_fail);
     cudaFreeHost(h->h_slots); cudaFreeHost(h->h_slot_phase);
     free_groups(h);
@@ -704,6 +706,8 @@ extern "C" int oi_run(oi_handle* h, const oi_params* p, const double* hypers_in)
     CK(cudaMemcpyAsync(h->ca.status, st0.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, h->st));
     CK(cudaMemcpyAsync(h->ca.nfev, nf0.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, h->st));
     CK(cudaMemcpyAsync(h->ca.phase, phase.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, h->st));
+    h->ca.dbg = h->d_dbg; h->ca.dbg_cell = h->dbg_cell; h->ca.dbg_cap = h->dbg_cap; h->ca.dbg_count = h->d_dbg_count;
+    if (h->d_dbg_count) CK(cudaMemsetAsync(h->d_dbg_count, 0, 4, h->st));
     if (p->mode == OI_MODE_FIT) {
         oi_launch_cg_init(h->ca, nc, rc, h->st);
         CK(cudaGetLastError());
@@ -730,6 +734,31 @@ extern "C" int oi_get_results(oi_handle* h, double* out, int32_t* n_out, int32_t
     if (nfev_out) CK(cudaMemcpy(nfev_out, h->ca.nfev, nc * 4, cudaMemcpyDeviceToHost));
     if (status_out) CK(cudaMemcpy(status_out, h->ca.status, nc * 4, cudaMemcpyDeviceToHost));
     if (n_out) std::memcpy(n_out, h->h_counts.data(), nc * 4);
+    return OI_OK;
+}
+
+// Diagnostic: record every objective evaluation (natural-unit hyperparameters, value, gradient) the optimiser of ONE cell
+// sees during the next oi_run(OI_MODE_FIT) calls.  cell < 0 switches it off.
+extern "C" int oi_debug_trace(oi_handle* h, int64_t cell, int32_t capacity) {
+    if (!h) return fail(OI_ERR_ARG, "oi_debug_trace: NULL handle");
+    CK(cudaSetDevice(h->device));
+    cudaFree(h->d_dbg); cudaFree(h->d_dbg_count); h->d_dbg = nullptr; h->d_dbg_count = nullptr; h->dbg_cell = -1; h->dbg_cap = 0;
+    if (cell < 0 || capacity <= 0) return OI_OK;
+    CK(cudaMalloc(&h->d_dbg, (size_t)capacity * 12 * 8));
+    CK(cudaMalloc(&h->d_dbg_count, 4));
+    CK(cudaMemset(h->d_dbg_count, 0, 4));
+    h->dbg_cell = (int)cell; h->dbg_cap = capacity;
+    return OI_OK;
+}
+extern "C" int oi_get_debug_trace(oi_handle* h, double* rows, int32_t* n_rows) {
+    if (!h || !rows || !n_rows) return fail(OI_ERR_ARG, "oi_get_debug_trace: NULL argument");
+    if (!h->d_dbg) return fail(OI_ERR_STATE, "oi_get_debug_trace: call oi_debug_trace first");
+    CK(cudaSetDevice(h->device));
+    int cnt = 0;
+    CK(cudaMemcpy(&cnt, h->d_dbg_count, 4, cudaMemcpyDeviceToHost));
+    cnt = std::min(cnt, h->dbg_cap);
+    if (cnt > 0) CK(cudaMemcpy(rows, h->d_dbg, (size_t)cnt * 12 * 8, cudaMemcpyDeviceToHost));
+    *n_rows = cnt;
     return OI_OK;
 }
 

@@ -78,6 +78,15 @@ __device__ __noinline__ int warp_finalize(const OiSlot s, const OiCellArrays ca,
             if (rc.grad_convention == 1) { g[3] /= 2; g[4] /= 2; }  // true derivatives
             g[5] = 0.0;
         }
+        if (ca.dbg && s.cell == ca.dbg_cell && phase == OI_PH_FIT) {
+            const int at = atomicAdd(ca.dbg_count, 1);
+            if (at < ca.dbg_cap) {
+                double* d = ca.dbg + 12 * (size_t)at;
+                for (int q = 0; q < 5; q++) d[q] = __ldcg(&h[q]);
+                d[5] = f;
+                for (int q = 0; q < OI_MAXH; q++) d[6 + q] = g[q];
+            }
+        }
         if (phase == OI_PH_EVAL) {
             ca.evf[s.cell] = f;
             for (int q = 0; q < OI_MAXH; q++) ca.evg[OI_MAXH * (size_t)s.cell + q] = g[q];

@@ -32,7 +32,10 @@ struct OiCellArrays {
     int* status;          // [n_cells]
     double* evf;          // [n_cells]    (OI_PH_EVAL)
     double* evg;          // [n_cells][6] (OI_PH_EVAL)
-    void* cg;             // [n_cells] OiCgState
+    void* cg;             // [n_cells] optimiser state (OiCgState or OiLbfgsState)
+    double* dbg;          // optional evaluation trace of ONE cell (oi_debug_trace): [cap][12] = hyp(5) | f | g(6)
+    int dbg_cell, dbg_cap;
+    int* dbg_count;
 };
 
 struct OiPacked {

@@ -132,6 +132,16 @@ class Handle:
         self._check(self._L.oi_get_results(self._h, _ptr(out), _ptr(n), _ptr(nfev), _ptr(status)))
         return dict(out=out, n=n, nfev=nfev, status=status)
 
+    def debug_trace(self, cell: int, capacity: int = 4096):
+        """Record every objective evaluation of one cell's optimiser during the next fits (diagnostic)."""
+        self._dbg_cap = int(capacity)
+        self._check(self._L.oi_debug_trace(self._h, int(cell), int(capacity)))
+
+    def get_debug_trace(self) -> np.ndarray:
+        rows = np.zeros((self._dbg_cap, 12)); n = C.c_int32(0)
+        self._check(self._L.oi_get_debug_trace(self._h, _ptr(rows), C.addressof(n)))
+        return rows[:n.value].copy()
+
     def stats(self) -> dict:
         s = _lib.OiStats()
         self._check(self._L.oi_get_stats(self._h, C.byref(s)))
@@ -173,8 +183,8 @@ class GPRDay:
                    day.x0, **kw)
 
     def _params(self, mode, **kw):
-        return self.handle.make_params(self.radius * 1000.0, self.T_mid, self.mean, self.x0, mode=mode,
-                                       grad_convention=self.grad_convention, **kw)
+        kw.setdefault("grad_convention", self.grad_convention)
+        return self.handle.make_params(self.radius * 1000.0, self.T_mid, self.mean, self.x0, mode=mode, **kw)
 
     def run(self, opt: bool = True, ellXs=None, sf2xs=None, sn2xs=None, **kw):
         """All cells at once.  opt=True: fit + predict (pass 1, GPR_CS2S3.py:258-262).  opt=False:

@@ -91,9 +91,11 @@ def run_season(obs, sie_mask, x, y, days, dates=None, grid_res: float = 25, T: i
     GPR_CS2S3.py:290-297, :303-307, :333-334); ``dates[day + T//2]`` names a day (default: the index)."""
     if x0 is None:
         x0 = [np.log(grid_res * 1000), np.log(grid_res * 1000), np.log(1.), np.log(1.), np.log(1.), np.log(.1)]   # :217
+    import time
     own = handle is None
     handle = handle or Handle(device)
     out = {}
+    timing = out.setdefault("_timing", {})        # per date: seconds of both passes, cells, non-finite cells
     try:
         if resident:
             handle.set_observations(*flatten_season(obs, x, y))          # once; every day only moves the window
@@ -105,12 +107,15 @@ def run_season(obs, sie_mask, x, y, days, dates=None, grid_res: float = 25, T: i
             else:
                 gd = GPRDay(g["x_train"], g["y_train"], g["t_train"], g["z"], g["X"], radius, g["mean"], g["T_mid"], x0,
                             handle=handle)
+            t0 = time.perf_counter()
             if smooth_pass:
                 res = two_pass(gd, g["ids"], g["SIE"].shape, g["SIE"], date=date, grid_res=grid_res, T=T, **run_kw)
                 res[date + "_diagnostics"] = res.pop("_diagnostics")
             else:
                 r1 = gd.run(opt=True, **run_kw)
                 res = assemble(r1["out"], g["ids"], g["SIE"].shape, date)
+            timing[date] = dict(day=int(day), seconds=time.perf_counter() - t0, cells=int(len(g["X"])),
+                                nonfinite=int(np.isnan(res[date + "_interp"][g["ids"]]).sum()))
             out.update(res)
     finally:
         if resident and not own:
@@ -118,3 +123,62 @@ def run_season(obs, sie_mask, x, y, days, dates=None, grid_res: float = 25, T: i
         if own:
             handle.close()
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: the winter season (~180 daily fields) on the 8 GPUs of one box.  Days are independent
+# (the reference script IS one day, GPR_CS2S3.py:211; the season is that script run per day), so the natural shard is
+# BY DAY: every rank holds the whole season's gridded observations (as every MPI rank of the reference loads all data,
+# :201-210), takes days[rank::world] and runs both passes for them on its own GPU.  No cost model is needed (a day is a
+# day), there is no per-day cross-rank tail, and the only exchange is the final collection of the per-day products.
+# ------------------------------------------------------------------------------------------------------------------
+def shard_days(days, rank: int, world: int) -> list:
+    """Round-robin: consecutive days (similar ice extent, similar cost) land on different ranks."""
+    return list(days)[rank::world]
+
+
+def run_season_sharded(obs, sie_mask, x, y, days, rank: int | None = None, world: int | None = None,
+                       collect: str = "summary", runner=None, **kw) -> dict:
+    """``run_season`` for this rank's share of ``days`` (one process per GPU, launched with torchrun).
+
+    collect: "summary" -- every rank returns its own days' fields plus, under ``_timing``, the per-day timing rows of
+             ALL ranks (one small all_gather_object); "all" -- additionally every rank receives every day's fields
+             (the reference's final ``COMM.bcast`` of the day dictionary, :311); "none" -- no collective at all.
+    Without an initialised process group it is ``run_season`` on one GPU.  ``runner`` (default ``run_season``) is the
+    per-rank worker; the CPU tests substitute it."""
+    import torch.distributed as dist
+    ddp = dist.is_available() and dist.is_initialized()
+    if rank is None:
+        rank = dist.get_rank() if ddp else 0
+    if world is None:
+        world = dist.get_world_size() if ddp else 1
+    mine = shard_days(days, rank, world)
+    runner = runner or run_season
+    out = runner(obs, sie_mask, x, y, mine, **kw) if mine else {"_timing": {}}
+    if ddp and world > 1 and collect != "none":
+        if collect == "all":
+            parts = [None] * world
+            dist.all_gather_object(parts, out)
+            merged = {"_timing": {}}
+            for p in parts:
+                merged["_timing"].update(p.pop("_timing"))
+                merged.update(p)
+            return merged
+        rows = [None] * world
+        dist.all_gather_object(rows, out["_timing"])
+        out["_timing"] = {k: v for r in rows for k, v in r.items()}
+    return out
+
+
+def make_synthetic_season(n_days: int, T: int = 9, **day_kw):
+    """Gridded observations, ice mask and lattice coordinates of a synthetic season with ``n_days`` interpolated days
+    (n_days + T - 1 days of tracks), in the layout ``readFB`` returns (GPR_CS2S3.py:25-63): obs (ny, nx, 4, days),
+    SIE (ny, nx, days) NaN off-ice, x / y (ny, nx)."""
+    from .synthetic import make_day
+    d = make_day(T=n_days + T - 1, keep_sat=True, **day_kw)
+    ny, nx = d.shape
+    res = d.grid_res_km * 1000.0
+    jj, ii = np.meshgrid(np.arange(nx), np.arange(ny))
+    sie = np.full((ny, nx, n_days + T - 1), np.nan)
+    sie[d.ids[0], d.ids[1], :] = 1.0
+    return d.sat, sie, res * jj.astype(np.float64), res * ii.astype(np.float64)

@@ -51,8 +51,11 @@ def make_day(n_side: int = 320, grid_res_km: float = 25.0, ice_radius_cells: flo
              centre: tuple = (137, 137), T: int = 9, radius_km: float = 300.0,
              tracks_per_day: int = 22, seed: int = 20190128, keep_sat: bool = False,
              s3_hole_cells: float = 38.0, cs2_hole_cells: float = 9.0,
-             noise_std: float = 0.04, thin_lo: float = 0.2) -> SyntheticDay:
-    """Build one synthetic day.  Defaults are BASELINE.json configs[1] (25 km pan-Arctic day)."""
+             noise_std: float = 0.04, thin_lo: float = 0.2, ice_mask: np.ndarray | None = None) -> SyntheticDay:
+    """Build one synthetic day.  Defaults are BASELINE.json configs[1] (25 km pan-Arctic day).
+
+    ice_mask: optional (n_side, n_side) bool array that replaces the ice disc, e.g. the real ice mask of a QuickLook
+    product (``files.quicklook_ice_mask``; SURVEY.md 8(d) option B): targets AND observations are confined to it."""
     res = grid_res_km * 1000.0
     jj, ii = np.meshgrid(np.arange(n_side), np.arange(n_side))
     x = res * jj.astype(np.float64)
@@ -60,6 +63,10 @@ def make_day(n_side: int = 320, grid_res_km: float = 25.0, ice_radius_cells: flo
     ci, cj = centre
     rad = np.hypot(ii - ci, jj - cj)
     ice = rad <= ice_radius_cells
+    if ice_mask is not None:
+        ice = np.asarray(ice_mask, dtype=bool)
+        if ice.shape != (n_side, n_side):
+            raise ValueError("ice_mask must be (n_side, n_side)")
     scale = grid_res_km / 25.0
     sat = np.full((n_side, n_side, 4, T), np.nan)
     # streams: 0 CS2 SAR, 1 CS2 SARIN, 2 S3A, 3 S3B  (GPR_CS2S3.py:57)
@@ -123,3 +130,17 @@ def make_day_cfg5(seed: int = 20190128, tracks_per_day: int = 17) -> SyntheticDa
     and track geometry as ``make_day`` in kilometres.  ~76k ice cells, ~60k observations, n per cell ~1500...5100."""
     return make_day(n_side=640, grid_res_km=12.5, ice_radius_cells=156.0, centre=(274, 274), radius_km=500.0,
                     tracks_per_day=tracks_per_day, seed=seed, s3_hole_cells=76.0, cs2_hole_cells=18.0)
+
+
+def make_day_real_mask(mask_npz: str, **kw) -> SyntheticDay:
+    """SURVEY.md 8(d) option B: the synthetic tracks of ``make_day`` over the REAL ice mask of a QuickLook day
+    (tests/golden/quicklook_icemask.npz, written by tests/golden/make_quicklook_mask.py; 17 697 ice cells on
+    2019-01-28, pole at lattice index (137, 137))."""
+    f = np.load(mask_npz)
+    shape = tuple(int(v) for v in f["shape"])
+    mask = np.unpackbits(f["packed"])[:shape[0] * shape[1]].reshape(shape).astype(bool)
+    ci, cj = (int(v) for v in f["pole_index"])
+    # track geometry: 34 tracks per platform and day within 110 cells of the pole (the mask reaches 137 cells out): n per
+    # cell 2 ... 2326, median 723, sum n^3 = 1.04x the disc day's -- ragged down to a handful of observations at the ice edge
+    kw.setdefault("ice_radius_cells", 110.0); kw.setdefault("tracks_per_day", 34)
+    return make_day(n_side=shape[0], centre=(ci, cj), ice_mask=mask, **kw)

@@ -62,7 +62,9 @@ def test_resident_season_equals_per_day_upload():
     b = run_season(obs, sie, x, y, days=[0, 2], radius=100, resident=False)
     assert set(a) == set(b)
     for k in b:
-        if k.endswith("_diagnostics"):
+        if k == "_timing":
+            assert set(a[k]) == set(b[k])
+        elif k.endswith("_diagnostics"):
             assert np.array_equal(a[k]["nfev"], b[k]["nfev"]) and np.array_equal(a[k]["status"], b[k]["status"])
         else:
             assert np.array_equal(a[k], b[k], equal_nan=True), k
@@ -100,3 +102,41 @@ def test_run_season_equals_day_by_day():
                 continue
             assert np.array_equal(season[k], v, equal_nan=True), k
         assert np.isfinite(season[date + "_interp_smth"][g["ids"]]).mean() > 0.9
+
+
+def _season_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    from optimalinterpolation_b200.season import run_season_sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def fake_runner(obs, sie, x, y, days, **kw):          # stands in for run_season (which needs a GPU)
+        out = {"_timing": {}}
+        for d in days:
+            out[f"{d}_interp"] = np.full((3, 3), float(d)); out["_timing"][str(d)] = dict(day=d, seconds=0.1 * d, cells=9, nonfinite=0)
+        return out
+    a = run_season_sharded(None, None, None, None, days=range(7), collect="summary", runner=fake_runner)
+    b = run_season_sharded(None, None, None, None, days=range(7), collect="all", runner=fake_runner)
+    q.put((rank, sorted(k for k in a if k != "_timing"), sorted(a["_timing"]), sorted(k for k in b if k != "_timing"), float(b["5_interp"][0, 0])))
+    dist.barrier(); dist.destroy_process_group()
+
+
+def test_season_sharded_by_day_world2_gloo():
+    """BASELINE.json configs[3]: days round-robin over ranks, one small collective for the per-day timing rows (or the
+    reference's final bcast of all fields with collect='all')."""
+    import socket
+    import torch.multiprocessing as mp
+    from optimalinterpolation_b200.season import shard_days
+    assert shard_days(range(7), 0, 2) == [0, 2, 4, 6] and shard_days(range(7), 1, 2) == [1, 3, 5]
+    assert sorted(sum((shard_days(range(180), r, 8) for r in range(8)), [])) == list(range(180))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_season_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = {r[0]: r[1:] for r in (q.get(timeout=120) for _ in range(2))}
+    [p.join(60) for p in procs]
+    assert got[0][0] == ["0_interp", "2_interp", "4_interp", "6_interp"] and got[1][0] == ["1_interp", "3_interp", "5_interp"]
+    assert got[0][1] == got[1][1] == [str(d) for d in range(7)]          # every rank sees every day's timing row
+    assert got[0][2] == got[1][2] == sorted(f"{d}_interp" for d in range(7)) and got[0][3] == got[1][3] == 5.0
