@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(OI_THREADS, OI_PIPE_MINB) k_chol_update(const 
 
 // Everything that only waits for Dinv[k]: the panel tiles (i, k), i > k, and -- row k of L being final once block
 // column k has been updated -- the row scaling Ls_kj = L_kk^-1 L_kj of row k (j < k).  One launch, no extra pass.
-__global__ void __launch_bounds__(OI_THREADS, 3) k_chol_panel(const OiSlot* __restrict__ slots, int k, int n_panel) {
+__global__ void __launch_bounds__(OI_THREADS, OI_PIPE_MINB) k_chol_panel(const OiSlot* __restrict__ slots, int k, int n_panel) {
     extern __shared__ __align__(16) double smem[];
     const OiSlot s = slots[blockIdx.y];
     if (k >= s.N) return;
@@ -132,17 +132,6 @@ __global__ void __launch_bounds__(256) k_fwd(const OiSlot* __restrict__ slots, O
     const OiSlot s = slots[blockIdx.x];
     if (OI_FAILED(s)) return;
     cell_fwd(s, ca, pk, t_pred, ca.phase[s.cell] == OI_PH_PREDICT, smem);
-}
-
-__global__ void __launch_bounds__(OI_THREADS, 3) k_scale_rows(const OiSlot* __restrict__ slots, int row) {
-    extern __shared__ __align__(16) double smem[];
-    const OiSlot s = slots[blockIdx.y];
-    int i, j;
-    if (row >= 0) { i = row; j = blockIdx.x; }
-    else { tile_ij(blockIdx.x, i, j); i += 1; }   // strictly lower tiles: (i, j), 1 <= i < N, j < i
-    if (i >= s.N) return;
-    if (OI_FAILED(s)) return;
-    tile_scale(s, i, j, smem);
 }
 
 __global__ void __launch_bounds__(OI_THREADS, OI_PIPE_MINB) k_trtri(const OiSlot* __restrict__ slots, const int* __restrict__ phase, int d) {
@@ -197,14 +186,12 @@ int oi_set_kernel_attributes() {
         if (e == cudaSuccess) e = r;
     };
     set((const void*)k_chol_update, OI_SMEM_PIPE);
-    set((const void*)k_chol_panel, OI_SMEM_BYTES);
+    set((const void*)k_chol_panel, OI_SMEM_PIPE);
     set((const void*)k_trtri, OI_SMEM_PIPE);
-    set((const void*)k_scale_rows, OI_SMEM_BYTES);
     set((const void*)k_lauum_trace, OI_SMEM_PIPE);
     return (int)e;
 }
 static_assert(OI_SMEM_PIPE == PIPE_BYTES, "pipeline size");
-static_assert(OI_SMEM_BYTES >= PIPE_BYTES && OI_SMEM_BYTES >= 2 * NB * TS * 8 + 4 * 64 * 8 + 16, "shared memory budget");
 static_assert(PIPE_BYTES >= NB * TS * 8 + 4 * 64 * 8 + 16, "packed diagonal block must fit the pipeline buffers");
 
 void oi_launch_count(const double* ox, const double* oy, const double* ot, int n_obs, const double* X, int n_cells, double r2,
@@ -240,7 +227,7 @@ void oi_launch_chol_update(const OiSlot* slots, int A, int Nmax, const int* cnt_
 void oi_launch_chol_panel(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int k, cudaStream_t st) {
     const int n_panel = cnt_gt[k + 1] > 0 ? Nmax - k - 1 : 0;     // panel tiles exist for cells with N > k+1, row k for N > k
     if (n_panel + k <= 0 || cnt_gt[k] <= 0) return;
-    k_chol_panel<<<dim3(n_panel + k, cnt_gt[k]), OI_THREADS, OI_SMEM_BYTES, st>>>(slots, k, n_panel);
+    k_chol_panel<<<dim3(n_panel + k, cnt_gt[k]), OI_THREADS, OI_SMEM_PIPE, st>>>(slots, k, n_panel);
 }
 void oi_launch_fwd(const OiSlot* slots, int A, OiCellArrays ca, OiPacked pk, double t_pred, cudaStream_t st) {
     k_fwd<<<A, 256, SMALL_SMEM, st>>>(slots, ca, pk, t_pred);
@@ -248,12 +235,6 @@ void oi_launch_fwd(const OiSlot* slots, int A, OiCellArrays ca, OiPacked pk, dou
 void oi_launch_trtri(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int d, const int* phase, cudaStream_t st) {
     if (Nmax - d <= 0 || cnt_gt[d] <= 0) return;
     k_trtri<<<dim3(Nmax - d, cnt_gt[d]), OI_THREADS, OI_SMEM_PIPE, st>>>(slots, phase, d);
-}
-void oi_launch_scale_rows(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, cudaStream_t st) {
-    if (Nmax < 2) return;
-    if (A >= OI_ROWWISE_MIN_SLOTS) {
-        for (int i = 1; i < Nmax; i++) k_scale_rows<<<dim3(i, cnt_gt[i]), OI_THREADS, OI_SMEM_BYTES, st>>>(slots, i);
-    } else k_scale_rows<<<dim3(Nmax * (Nmax - 1) / 2, A), OI_THREADS, OI_SMEM_BYTES, st>>>(slots, -1);
 }
 void oi_launch_alpha(const OiSlot* slots, int A, int Nmax, const int* phase, cudaStream_t st) {
     k_alpha<<<dim3(Nmax, A), OI_THREADS, 0, st>>>(slots, phase);

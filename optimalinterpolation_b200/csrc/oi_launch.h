@@ -6,7 +6,6 @@
 #define OI_THREADS 128                 // threads of every tile CTA (4 warps, 2x2 warp tiles of 32x32)
 #define OI_ROWWISE_MIN_SLOTS_HOST 96   // batches at least this big launch the tile-parallel kernels one block row at a time
 #define OI_DEFAULT_GROUPS 8
-#define OI_SMEM_BYTES (2 * OI_NB * 68 * 8 + 4 * 64 * 8 + 16)   // T + W of the diagonal factor + per-warp scratch + flag (>= the cp.async pipeline)
 #ifndef STAGES
 #define STAGES 3
 #endif
@@ -27,7 +26,6 @@ void oi_launch_pack(const int* indices, long long total, const double* ox, const
 void oi_launch_build(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, OiCellArrays ca, OiPacked pk, cudaStream_t st);
 void oi_launch_chol_update(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int k, cudaStream_t st);
 void oi_launch_chol_panel(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int k, cudaStream_t st);
-void oi_launch_scale_rows(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, cudaStream_t st);
 void oi_launch_fwd(const OiSlot* slots, int A, OiCellArrays ca, OiPacked pk, double t_pred, cudaStream_t st);
 void oi_launch_trtri(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, int d, const int* phase, cudaStream_t st);
 void oi_launch_alpha(const OiSlot* slots, int A, int Nmax, const int* phase, cudaStream_t st);

@@ -261,7 +261,12 @@ __device__ __forceinline__ void pivot_factor_invert(double* P, int jb, int lane,
         }
         double piv = __shfl_sync(0xffffffffu, a[c], c, 8);
         if (piv <= 0.0) bad = true;
-        double sq = sqrt(piv), inv = 1.0 / sq;
+        // 1/sqrt(piv) first, then sqrt(piv) = piv * (1/sqrt(piv)): the 64 pivots of a diagonal block are one dependent chain
+        // (the critical path of the optimiser's tail, where a handful of small cells iterate at kernel latency), and
+        // sqrt followed by a division is the longest link of it.  rsqrt is within 1 ulp, the product adds half an ulp: far inside
+        // the 1e-9 parity gate (measured 1e-14), not IEEE sqrt.  piv = +inf gives NaN here and inf in LAPACK; both end in
+        // a NaN objective.
+        double inv = rsqrt(piv), sq = piv * inv;
         dinv[c] = inv;
         if (r == c) a[c] = sq;
         else if (r > c) a[c] *= inv;
@@ -580,38 +585,66 @@ __device__ __forceinline__ void cell_fwd(const OiSlot& s, const OiCellArrays& ca
 // kernel (3c'): row scaling  Ls_ij = L_ii^-1 * L_ij  (i > j), in place.
 // With it the forward substitution and the inverse need no per-step triangular solve:
 //   t_i = L_ii^-1 r_i - sum_{j<i} Ls_ij t_j            W_ik = -sum_{j=k}^{i-1} Ls_ij W_jk
-// smem: 2*NB*TS doubles.
+// An "NN" product out[m][n] = sum_kk Dinv_i[m][kk] L_ij[kk][n] (the second operand is not K-contiguous), streamed through
+// the same STAGES-deep cp.async pipeline as the NT tiles (smem: PIPE_BYTES, so the panel kernel keeps 4 CTAs/SM):
+//   A chunk = Dinv_i[:, c:c+16]   64 rows x 16, the usual XOR-swizzled layout
+//   B chunk = L_ij[c:c+16, :]     16 rows (kk) x 64 cols (n); element (kk, n) is stored at kk*64 + (n ^ ((kk & 3) << 2)):
+//                                 the DMMA B fragment (4 consecutive kk x 8 consecutive n per instruction) then touches 16
+//                                 distinct double-banks per half-warp, and 16-byte cp.async pieces stay whole.
+// Dinv_i is lower triangular: output row m only needs kk <= m; rows of L_ij beyond the cell's size are zero.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_stage_nn(double* st, const double* __restrict__ A, const double* __restrict__ B, long long ldb,
+                                              int kk0, int tid) {
+    double* As = st;
+    double* Bs = st + NB * KT;
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+        const int c = tid + it * GEMM_THREADS;      // 0..511
+        {
+            const int row = c >> 3, p = c & 7;      // A: 64 rows x 8 pieces
+            cp_async16(&As[row * KT + ((p ^ (row & 7)) << 1)], &A[row * NB + kk0 + p * 2]);
+        }
+        {
+            const int kk = c >> 5, p = c & 31;      // B: 16 rows x 32 pieces
+            cp_async16(&Bs[kk * NB + ((p * 2) ^ ((kk & 3) << 2))], &B[(long long)(kk0 + kk) * ldb + p * 2]);
+        }
+    }
+}
+
 __device__ __forceinline__ void tile_scale(const OiSlot& s, int i, int j, double* smem) {
     const long long ld = s.npad;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 1, wn = warp & 1;
-    double* TA = smem;             // Dinv_i [m][kk]
-    double* TB = smem + NB * TS;   // L_ij   [kk][n]
+    const int fr = lane >> 2, fc = lane & 3;
     const double* Di = s.Dinv + (long long)i * OI_TILE;
     double* Lg = s.M + (long long)i * NB * ld + (long long)j * NB;
-    __syncthreads();
-    for (int idx = tid; idx < OI_TILE / 2; idx += GEMM_THREADS) {
-        int r = idx >> 5, c = (idx & 31) * 2;
-        cp_async16(&TA[r * TS + c], &Di[r * NB + c]);
-        cp_async16(&TB[r * TS + c], &Lg[(long long)r * ld + c]);
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
     double acc[4][4][2];
     ACC_ZERO(acc);
-    const int vi = s.n16 - i * NB;              // valid rows of block i
-    const int fr = lane >> 2, fc = lane & 3;
-    // out[m][n] = sum_kk Dinv_i[m][kk] L_ij[kk][n], Dinv_i lower triangular: row m needs kk <= m
-    for (int c = 0; c < NB && c < vi; c += KT) {
-        const int mlo = lo_ge(wm, c), mhi = hi_lt(wm, vi);
+    const int vi = min(NB, s.n16 - i * NB);     // valid rows of block i (a multiple of 16)
+    const int nk = vi / KT;
+    const int mhi = hi_lt(wm, vi);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < STAGES - 1; q++) {
+        if (q < nk) load_stage_nn(smem + q * STAGE_DOUBLES, Di, Lg, ld, q * KT, tid);
+        cp_async_commit();
+    }
+    for (int it = 0; it < nk; it++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        const int nx = it + STAGES - 1;
+        if (nx < nk) load_stage_nn(smem + (nx % STAGES) * STAGE_DOUBLES, Di, Lg, ld, nx * KT, tid);
+        cp_async_commit();
+        const double* As = smem + (it % STAGES) * STAGE_DOUBLES;
+        const double* Bs = As + NB * KT;
+        const int mlo = lo_ge(wm, it * KT);
 #pragma unroll
         for (int ks = 0; ks < KT / 4; ks++) {
             double a[4], b[4];
+            const int sw = (((ks * 2 + (fc >> 1)) ^ fr) << 1) + (fc & 1);
 #pragma unroll
-            for (int mb = 0; mb < 4; mb++) a[mb] = TA[(wm * 32 + mb * 8 + fr) * TS + c + ks * 4 + fc];
+            for (int mb = 0; mb < 4; mb++) a[mb] = As[(wm * 32 + mb * 8 + fr) * KT + sw];
 #pragma unroll
-            for (int nb = 0; nb < 4; nb++) b[nb] = TB[(c + ks * 4 + fc) * TS + wn * 32 + nb * 8 + fr];
+            for (int nb = 0; nb < 4; nb++) b[nb] = Bs[(ks * 4 + fc) * NB + ((wn * 32 + nb * 8 + fr) ^ (fc << 2))];
 #pragma unroll
             for (int mb = 0; mb < 4; mb++)
                 if (mb >= mlo && mb < mhi) {
@@ -620,6 +653,8 @@ __device__ __forceinline__ void tile_scale(const OiSlot& s, int i, int j, double
                 }
         }
     }
+    cp_async_wait<0>();
+    __syncthreads();
 #pragma unroll
     for (int mb = 0; mb < 4; mb++)
 #pragma unroll

@@ -2,15 +2,8 @@
 
 TEST/BENCH INFRASTRUCTURE ONLY.  Mirrors the reference's one-MPI-rank-per-core data parallelism
 over cells (GPR_CS2S3.py:18-23, :250-262) with multiprocessing, one BLAS thread per worker
-(mpi4py/mpirun are not installed).  A full day is hundreds of CPU-hours, so a bounded sample is timed.
-
-``run_eval_sample`` (used by bench.py): the reference spends > 99 % of its time inside ``SMLII`` evaluations
-(SURVEY.md 8a), so one evaluation is timed on cells taken at evenly spaced quantiles of the workload's
-n-distribution (smallest to largest, one cell per core), a power law t(n) = a n^p is fitted to those timings, and
-the workload's cost is sum_c (nfev_c + 1/3) * t(n_c) core-seconds (nfev_c = evaluations the optimiser needs for
-cell c, measured; the final prediction costs about a third of an evaluation).  Extrapolating whole fits of the
-cheapest cells by n^3 -- ``run_sample``, the earlier estimate -- undercounts the CPU by ~3x because the measured
-exponent is ~2.4, not 3.
+(mpi4py/mpirun are not installed).  A full day is hundreds of CPU-hours, so a bounded sample of whole fits is timed
+(``run_boxed_fits`` below; round 1's power-law model of single evaluations was replaced by it).
 """
 from __future__ import annotations
 
@@ -42,80 +35,6 @@ def _work(index):
     t0 = time.perf_counter()
     out, res = _G["o"].gpr3d(int(index), return_result=True)
     return int(index), tuple(float(v) for v in out), int(res.nfev), time.perf_counter() - t0
-
-
-def choose_sample(counts, cells, n_sample, frac):
-    """``n_sample`` cells evenly spaced over the cheapest ``frac`` of ``cells`` (sorted by n)."""
-    cells = np.asarray(cells)
-    order = cells[np.argsort(counts[cells], kind="stable")]
-    top = max(n_sample, int(len(order) * frac))
-    pick = np.unique(np.linspace(0, top - 1, n_sample).round().astype(int))
-    return order[pick]
-
-
-def run_sample(day, counts, cells, cores=None, frac=0.25, n_sample=None, x0=None):
-    """Time the oracle's GPR3D on a bounded sample.  Returns a dict with cells/s scaled to the
-    cost mix of ``cells`` and a description of the sample."""
-    cores = cores or os.cpu_count() or 1
-    n_sample = n_sample or cores
-    x0 = list(day.x0 if x0 is None else x0)
-    sample = choose_sample(counts, cells, n_sample, frac)
-    arrays = (day.x_train, day.y_train, day.t_train, day.z, day.X, day.radius_km, day.mean, day.T_mid)
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_init, initargs=(arrays, x0)) as pool:
-        pool.map(_work, [int(sample[0])] * 0)          # spin the workers up
-        t0 = time.perf_counter()
-        rows = pool.map(_work, [int(c) for c in sample], chunksize=1)
-        wall = time.perf_counter() - t0
-    n3_sample = float(np.mean(counts[sample].astype(np.float64) ** 3))
-    n3_work = float(np.mean(counts[np.asarray(cells)].astype(np.float64) ** 3))
-    raw = len(sample) / wall
-    return dict(value=raw * n3_sample / n3_work, raw_cells_per_s=raw, wall_s=wall, cores=cores,
-                n_sample=len(sample), n_min=int(counts[sample].min()), n_max=int(counts[sample].max()),
-                cost_ratio=n3_sample / n3_work, nfev_mean=float(np.mean([r[2] for r in rows])),
-                rows=rows)
-
-
-def _eval_work(args):
-    index, reps = args
-    o = _G["o"]
-    from oracle.gpr_oracle import nlml_grad
-    _, inp, out, _ = o.cell_data(int(index))
-    mX = np.ones(len(out)) * o.mean
-    h = np.array(o.x0, dtype=float)
-    nlml_grad(h, inp, out, mX)                         # warm (allocations, BLAS)
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        nlml_grad(h, inp, out, mX)
-    return int(index), len(out), (time.perf_counter() - t0) / reps
-
-
-def run_eval_sample(day, counts, cells, nfev, cores=None, reps=1, x0=None):
-    """cells/s of the reference path on ``cores`` host cores for the workload ``cells`` (see module docstring).
-
-    nfev: per-cell evaluation counts (array aligned with ``cells``) or one mean value."""
-    cores = cores or os.cpu_count() or 1
-    x0 = list(day.x0 if x0 is None else x0)
-    cells = np.asarray(cells)
-    order = cells[np.argsort(counts[cells], kind="stable")]
-    pick = np.unique(np.linspace(0, len(order) - 1, cores).round().astype(int))
-    sample = order[pick]
-    arrays = (day.x_train, day.y_train, day.t_train, day.z, day.X, day.radius_km, day.mean, day.T_mid)
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_init, initargs=(arrays, x0)) as pool:
-        t0 = time.perf_counter()
-        # largest cells first so that the longest jobs do not start last
-        rows = pool.map(_eval_work, [(int(c), reps) for c in sample[::-1]], chunksize=1)
-        wall = time.perf_counter() - t0
-    n_s = np.array([r[1] for r in rows], dtype=float); t_s = np.array([r[2] for r in rows])
-    p, loga = np.polyfit(np.log(n_s), np.log(t_s), 1)
-    n_all = counts[cells].astype(float)
-    t_all = np.exp(loga) * n_all ** p
-    nf = np.broadcast_to(np.asarray(nfev, dtype=float), n_all.shape)
-    core_seconds = float(np.sum((nf + 1.0 / 3.0) * t_all))
-    return dict(value=len(cells) * cores / core_seconds, cores=cores, wall_s=wall, n_sample=len(sample),
-                n_min=int(n_s.min()), n_max=int(n_s.max()), exponent=float(p), t_eval_median_n=float(np.exp(loga) * np.median(n_all) ** p),
-                core_hours=core_seconds / 3600.0, nfev_mean=float(nf.mean()), rows=rows)
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -150,34 +150,35 @@ def test_cholesky_failure_semantics(small_day):
     h.close()
 
 
-def test_fit_matches_oracle(small_day, small_oracle):
-    """Fitted path: device lockstep scipy-CG vs scipy.optimize.minimize(CG) on the oracle objective."""
+def test_fit_matches_oracle(small_day):
+    """Fitted path on the small day: device lockstep scipy-CG vs the reference path (tests/golden/small_day_fit.npz:
+    scipy.optimize.minimize(CG) on the oracle objective for every 4th cell, in the reference's neighbour order and in
+    ascending order).  Small cells (n ~ 40...300) are where the reference's line searches are most chaotic:
+    the reference misses BASELINE.json's gate against ITSELF (tree order vs sorted order) on several per cent of them, so
+    the gate is the reference's own miss rate + 0.1 % + 2 sigma of the sample; see tests/test_gpu_fit_parity.py for the
+    full-size fixture."""
+    import os
     import optimalinterpolation_b200 as oi
-    d, o = small_day, small_oracle
-    cells = np.arange(0, len(d.X), 12)
+    from test_gpu_fit_parity import compare, summary
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "small_day_fit.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/small_day_fit.npz not generated")
+    fx = np.load(path)
+    d = small_day
+    cells = fx["cells"]
     g = oi.GPRDay(d.x_train, d.y_train, d.t_train, d.z, d.X[cells], d.radius_km, d.mean, d.T_mid, d.x0)
     res = g.run(opt=True)
-    out = res["out"]
-    dfs, ok_nl, both_nan = [], [], 0
-    for k, c in enumerate(cells):
-        ref, r = o.gpr3d(int(c), sort=True, return_result=True)
-        if np.isnan(ref[0]) or np.isnan(out[k, 0]):
-            # scipy ended on a NaN iterate (status 3): the reference returns the NaN tuple, so must we
-            both_nan += int(np.isnan(ref[0]) and np.isnan(out[k, 0]))
-            dfs.append(0.0 if (np.isnan(ref[0]) and np.isnan(out[k, 0])) else np.inf)
-            ok_nl.append(np.isnan(ref[0]) and np.isnan(out[k, 0]))
-            continue
-        dfs.append(abs(out[k, 0] - ref[0]) * 1000.0)
-        rel = (out[k, 2] - ref[2]) / abs(ref[2])      # lZ = -NLML: higher is better
-        ok_nl.append(rel > -1e-6)
-    dfs = np.array(dfs)
-    print(f"fit parity over {len(cells)} cells: |dfs| mm median {np.median(dfs):.3e} max {dfs.max():.3e}; "
-          f"frac <=1mm {np.mean(dfs <= 1.0):.3f}; NLML-ok frac {np.mean(ok_nl):.3f}; both-NaN {both_nan}; "
-          f"nfev mean {res['nfev'].mean():.1f}")
-    # the reference's stopping point is not invariant to 1e-16 perturbations (SURVEY.md C.8), so a
-    # small tail of cells may land elsewhere; on this 52-cell sample allow 3 of them
-    assert np.mean(dfs <= 1.0) >= 0.94
-    assert np.mean(ok_nl) >= 0.90
+    g.handle.close()
+    floor = compare(fx["out_sorted"], fx["out_tree"])
+    gpu = compare(res["out"], fx["out_tree"])
+    N = len(cells)
+    miss_floor, miss_gpu = 1 - floor["ok"].mean(), 1 - gpu["ok"].mean()
+    sigma = np.sqrt(max(miss_floor, 1.0 / N) * (1 - miss_floor) / N)
+    print(f"small-day fit parity over {N} cells: reference sorted-vs-tree {summary(floor)}\n GPU vs tree {summary(gpu)}\n"
+          f" miss rate GPU {miss_gpu:.4f} reference floor {miss_floor:.4f} sigma {sigma:.4f}; nfev mean GPU {res['nfev'].mean():.1f} "
+          f"ref {fx['nfev_tree'].mean():.1f}")
+    assert miss_gpu <= miss_floor + 0.001 + 2 * sigma
+    assert np.nanmedian(gpu["dfs"]) < 1e-3          # and the typical cell agrees to round-off
 
 
 def test_groupings_bit_identical(small_day):

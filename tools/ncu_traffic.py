@@ -12,7 +12,7 @@ for r in rows:
     acc[name][metric] += val * scale
     if metric == "gpu__time_duration.sum":
         acc[name]["launches"] += 1
-fam = ("k_chol_update", "k_chol_panel", "k_scale_rows", "k_trtri", "k_lauum_trace")
+fam = ("k_chol_update", "k_chol_panel", "k_trtri", "k_lauum_trace")
 out = {"per_kernel": {}, "source": sys.argv[1]}
 for k, v in sorted(acc.items(), key=lambda kv: -kv[1]["gpu__time_duration.sum"]):
     out["per_kernel"][k] = {"launches": int(v["launches"]), "us": v["gpu__time_duration.sum"],
