@@ -5,10 +5,13 @@ oracle/reference_functions.py) on seeded synthetic cells.  Run in the build cont
     python tests/golden/make_golden.py
 
 The fixture pins the oracle (oracle/gpr_oracle.py) and, through it, the CUDA path, on machines
-where /root/reference does not exist (the GPU box).  Library versions are stored in the file.
+where /root/reference does not exist (the GPU box).  Library versions and the BLAS thread count (the last bits of the
+LAPACK results depend on it) are stored in the file; tests/conftest.py runs the CPU suite with the same setting.
 """
 import os
 import sys
+
+os.environ["OPENBLAS_NUM_THREADS"] = "1"      # before numpy loads OpenBLAS
 
 import numpy as np
 import scipy
@@ -58,6 +61,7 @@ def main():
     ns["sn2xs"] = np.full(len(d.X), 0.00346)
     for c in CELLS:
         out[f"gpr3d_fixed_{c}"] = np.array(ns["GPR3D"](c, opt=False), dtype=float)
+    out["blas_threads"] = os.environ["OPENBLAS_NUM_THREADS"]
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors.npz"), **out)
     print("wrote", len(out), "arrays")
 

@@ -20,7 +20,10 @@ def gold():
 
 def _same_libs(gold):
     import scipy
-    return str(gold["numpy"]) == np.__version__ and str(gold["scipy"]) == scipy.__version__
+    # bit-identity needs the same libraries AND the same BLAS thread count (recorded in the fixture; conftest.py sets it)
+    import os
+    return (str(gold["numpy"]) == np.__version__ and str(gold["scipy"]) == scipy.__version__
+            and "blas_threads" in gold.files and str(gold["blas_threads"]) == os.environ.get("OPENBLAS_NUM_THREADS", ""))
 
 
 def test_neighbours_match_golden(gold, small_day, small_oracle):
