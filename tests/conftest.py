@@ -1,7 +1,15 @@
 import os
 import sys
 
-os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")   # the oracle's cells are small; BLAS threads only fight each other
+# One BLAS thread: the oracle's cells are small (threads only fight each other) and the last bits of LAPACK results
+# depend on the thread count, which tests/golden/reference_vectors.npz records.  A pytest plugin may have loaded numpy
+# (and OpenBLAS) before this file runs, so the limit is also applied at run time.
+os.environ["OPENBLAS_NUM_THREADS"] = "1"
+try:
+    from threadpoolctl import threadpool_limits
+    _BLAS_LIMIT = threadpool_limits(limits=1)
+except Exception:       # pragma: no cover
+    _BLAS_LIMIT = None
 
 import pytest
 
