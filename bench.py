@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--optimiser", default="cg", choices=["cg", "lbfgs"],
                     help="cg = the reference's scipy-CG restatement (parity mode, the headline); lbfgs = exact-gradient L-BFGS fast mode")
     ap.add_argument("--stripes-per-gpu", type=int, default=2)
+    ap.add_argument("--sharding", default="dynamic", choices=["dynamic", "lpt"],
+                    help="N>1: dynamic = one cost-sorted work list shared by the ranks (POSIX shared memory), lpt = static LPT split on n^3")
     ap.add_argument("--max-active", type=int, default=0)
     ap.add_argument("--budget-s", type=float, default=float(os.environ.get("OI_BENCH_BUDGET_S", 520)),
                     help="wall-clock budget of the whole run; the optional passes after the timed loop only start while it allows")
@@ -199,7 +201,7 @@ def main():
     import torch
     import torch.distributed as dist
     import optimalinterpolation_b200 as oi
-    from optimalinterpolation_b200.shard import gather_results
+    from optimalinterpolation_b200.shard import gather_results, gather_owned
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -234,7 +236,19 @@ def main():
     h.set_cells(Xstep)
     counts_step = h.gather_neighbours(day.radius_km * 1000.0).copy()
     config, parts = make_config(args, world, day, cells, counts_step)
-    mine = parts[rank]
+    dynamic = world > 1 and args.sharding == "dynamic"
+    if dynamic:
+        # every rank runs ALL cells of the step through one shared cost-sorted work list (csrc/oi_shared_queue.h): the same
+        # fresh segment name on every rank, attached before the first run
+        name = [f"/oi_b200_bench_{os.getpid()}_{int(time.time())}"]
+        dist.broadcast_object_list(name, src=0)
+        h.set_shared_queue(name[0])
+        dist.barrier()
+        mine = np.arange(len(cells))
+        config["sharding"] = (f"dynamic: one cost-sorted work list shared by the {world} ranks (largest cells claimed from the front, smallest "
+                              f"from the back; 64-bit cursor word in POSIX shared memory), every rank holds all {len(cells)} cells")
+    else:
+        mine = parts[rank]
     Xmine = pinned(Xstep[mine])
     fast = args.optimiser == "lbfgs"
     params = h.make_params(day.radius_km * 1000.0, day.T_mid, day.mean, day.x0, mode=0, max_active=args.max_active,
@@ -243,7 +257,11 @@ def main():
     def step():
         res = h.gpr_day(px, py, pt, pz, Xmine, params)
         st = h.stats()
-        full = gather_results(res["out"], mine, len(cells), parts)
+        if dynamic:
+            full, owned_counts = gather_owned(res["out"], h.get_owned())
+            res["owned_counts"] = owned_counts
+        else:
+            full = gather_results(res["out"], mine, len(cells), parts)
         return res, st, full
 
     for _ in range(args.warmup):
@@ -276,7 +294,7 @@ def main():
     step_s = e2e_ms * 1e-3 / args.steps
     h2d = 4 * day.z.size * 8 + Xmine.size * 8
     d2h = len(mine) * (64 + 12)
-    status_hist = np.bincount(res["status"], minlength=6).tolist()
+    status_hist = np.bincount(res["status"][h.get_owned()] if dynamic else res["status"], minlength=6).tolist()
 
     solo = world == 1
     # ---------------- CPU baseline: bounded sample of whole fits on the host cores (rank 0, N=1 only) ----------------
@@ -370,11 +388,14 @@ def main():
             "value_is": "the same timed steps without the host<->device copies: oi_stats.ms_gather + ms_total (CUDA events on the "
                         "library's launching stream, first gather kernel to last result), max over ranks per step",
             "gpu_launches": int(launches.item()),
-            "nfev_mean": float(res["nfev"].mean()), "evals_per_step": agg["n_evals"] / args.steps,
+            "nfev_mean": float(res["nfev"][h.get_owned()].mean() if dynamic else res["nfev"].mean()),
+            "cells_per_rank_last_step": [int(v) for v in res["owned_counts"]] if dynamic else [len(p) for p in parts], "evals_per_step": agg["n_evals"] / args.steps,
             "iterations_per_step": agg["n_iterations"] / args.steps,
             "status_hist_rank0": status_hist, "finite_frac": float(np.isfinite(full[:, 0]).mean()),
             "per_rank_device_ms_per_step": [float(v) for v in rank_ms.tolist()],
-            "limiter": ("the step ends with the slowest rank's optimiser tail: LPT balances n^3 but a cell costs n^3 x its evaluation "
+            "limiter": ("FP64 DMMA issue rate; the ranks draw from one shared work list and end within one cell's run time of each other "
+                        "(per_rank_device_ms_per_step)" if dynamic else
+                        "the step ends with the slowest rank's optimiser tail: LPT balances n^3 but a cell costs n^3 x its evaluation "
                         "count (65...2200); see per_rank_device_ms_per_step") if world > 1 else
                        "FP64 DMMA issue rate in the bulk, dependent-launch latency of the last long optimiser runs in the tail",
             "roofline": roofline,
@@ -385,6 +406,11 @@ def main():
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
+    if dynamic:
+        dist.barrier()
+        h.set_shared_queue(None)
+        if rank == 0:
+            h.unlink_shared_queue(name[0])
     h.close()
     if world > 1:
         dist.barrier()

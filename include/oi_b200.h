@@ -142,6 +142,16 @@ int oi_run(oi_handle* h, const oi_params* p, const double* hypers_in);
 /* out[n_cells][8]; nfev_out/status_out/n_out[n_cells] may be NULL. */
 int oi_get_results(oi_handle* h, double* out, int32_t* n_out, int32_t* nfev_out, int32_t* status_out);
 int oi_get_stats(oi_handle* h, oi_stats* s);
+/* Several GPU processes of ONE box (one per GPU) share one cost-sorted work list instead of a static split of the cells
+ * (reference: split(container, count), GPR_CS2S3.py:18-23, :250-256): a 64-bit word in POSIX shared memory holds the two
+ * cursors of the list, the largest cells are claimed from the front, the smallest from the back, each cell is computed by
+ * exactly one process (csrc/oi_shared_queue.h).  Every process calls oi_set_shared_queue with the same fresh, unique name
+ * ("/something") before its first oi_run and then runs the SAME calls on the SAME observations and cells; oi_get_owned
+ * tells which rows of oi_get_results are this process's (the others are NaN).  NULL detaches; oi_unlink_shared_queue removes
+ * the segment (one process, at the end). */
+int oi_set_shared_queue(oi_handle* h, const char* shm_name);
+int oi_unlink_shared_queue(const char* shm_name);
+int oi_get_owned(oi_handle* h, uint8_t* owned);
 /* Diagnostic (tools/cg_diagnose.py): record every objective evaluation the optimiser of ONE cell sees during the next
  * OI_MODE_FIT runs -- rows of 12 doubles: natural-unit hyperparameters (5), value, gradient (6).  cell < 0: off. */
 int oi_debug_trace(oi_handle* h, int64_t cell, int32_t capacity);

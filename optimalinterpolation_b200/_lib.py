@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "liboi_b200.so")
 
 EXPORTS = ("oi_version", "oi_last_error", "oi_create", "oi_destroy", "oi_set_observations", "oi_set_cells",
            "oi_gather_neighbours", "oi_get_neighbours", "oi_nlml_grad", "oi_run", "oi_get_results",
-           "oi_get_stats", "oi_gpr_day", "oi_set_stream", "oi_sizeof_params", "oi_sizeof_stats", "oi_set_time_window", "oi_debug_trace", "oi_get_debug_trace")
+           "oi_get_stats", "oi_gpr_day", "oi_set_stream", "oi_sizeof_params", "oi_sizeof_stats", "oi_set_time_window", "oi_debug_trace", "oi_get_debug_trace",
+           "oi_set_shared_queue", "oi_unlink_shared_queue", "oi_get_owned")
 
 
 class OiParams(C.Structure):
@@ -75,6 +76,9 @@ def load():
     L.oi_get_stats.argtypes = [vp, C.POINTER(OiStats)]
     L.oi_gpr_day.argtypes = [vp, dp, dp, dp, dp, C.c_int64, dp, C.c_int64, C.POINTER(OiParams), dp, dp, ip, ip, ip]
     L.oi_debug_trace.argtypes = [vp, C.c_int64, C.c_int32]
+    L.oi_set_shared_queue.argtypes = [vp, C.c_char_p]
+    L.oi_unlink_shared_queue.argtypes = [C.c_char_p]
+    L.oi_get_owned.argtypes = [vp, dp]
     L.oi_get_debug_trace.argtypes = [vp, dp, ip]
     L.oi_sizeof_params.restype = C.c_int
     L.oi_sizeof_stats.restype = C.c_int

@@ -17,6 +17,7 @@
 #include "oi_launch.h"
 #include "cg_scipy.h"
 #include "lbfgs_fast.h"
+#include "oi_shared_queue.h"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -58,6 +59,8 @@ struct oi_handle {
     oi_stats stats{};
     bool have_results = false;
     double* d_dbg = nullptr; int* d_dbg_count = nullptr; int dbg_cell = -1, dbg_cap = 0;
+    OiSharedQueue queue;                 // work list shared with the other GPU processes of the box (oi_set_shared_queue)
+    std::vector<uint8_t> owned;          // cells this handle computed in the last oi_run
 };
 
 struct OiGroup;
@@ -133,6 +136,7 @@ extern "C" void oi_destroy(oi_handle* h) {
     free_cells(h);
     cudaFree(h->indices); cudaFree(h->px); cudaFree(h->py); cudaFree(h->pt); cudaFree(h->pr);
     cudaFree(h->d_dbg); cudaFree(h->d_dbg_count);
+    h->queue.detach();
     cudaFree(h->arena); cudaFree(h->d_slots); cudaFree(h->d_slot_phase); cudaFree(h->d_fail);
     cudaFreeHost(h->h_slots); cudaFreeHost(h->h_slot_phase);
     free_groups(h);
@@ -311,6 +315,19 @@ struct LockstepRun {
     std::vector<int> pending; size_t next = 0, back = 0;
     int n_small = 0;
     bool takes_small(int gi) const { return !is_express(gi) && gi >= G - n_express - n_small; }
+    // With a shared queue (several GPU processes of one box) the two cursors live in shared memory and every rank claims
+    // from the same list (oi_shared_queue.h); without, they are the local next/back.
+    OiSharedQueue* q = nullptr;
+    long peek(bool small_end) const {
+        if (q) return small_end ? q->peek_back() : q->peek_front();
+        return next < back ? (long)(small_end ? back - 1 : next) : -1;
+    }
+    bool claim(bool small_end, long idx) {
+        if (q) return small_end ? q->claim_back(idx) : q->claim_front(idx);
+        if (small_end) back--; else next++;
+        return true;
+    }
+    bool list_empty() const { return peek(false) < 0; }
     OiPacked pk; FILE* trace = nullptr;
     double ms_factor = 0;
     // express lanes: the last n_express groups only take cells that already spent express_after iterations in a
@@ -355,18 +372,21 @@ struct LockstepRun {
         const int cap = is_express(gi) ? std::min(express_cap, g.slot_cap) : g.slot_cap;
         if (!is_express(gi)) {
             const bool small_end = takes_small(gi);
-            while (next < back && (int)g.active.size() < cap) {
-                const int c = small_end ? pending[back - 1] : pending[next];
+            while ((int)g.active.size() < cap) {
+                const long idx = peek(small_end);
+                if (idx < 0) break;
+                const int c = pending[(size_t)idx];
                 size_t need = slot_bytes(h->h_counts[c]);
                 if (g.used + need > g.arena_bytes) break;
                 if (!g.active.empty() && g.tiles + cell_tiles(c) > tile_budget) break;   // enough work to fill the GPU share
+                if (!claim(small_end, idx)) continue;                                     // another rank was faster: look again
                 g.used += need; g.tiles += cell_tiles(c); g.active.push_back(c);
-                if (small_end) back--; else next++;
+                h->owned[(size_t)c] = 1;
             }
         }
         // express cells go to the express lanes; once the bulk list is exhausted, bulk groups whose own batch has
         // become small help out
-        if (is_express(gi) || (next >= back && (int)g.active.size() < express_cap)) {
+        if (is_express(gi) || (list_empty() && (int)g.active.size() < express_cap)) {
             const int xcap = std::min(cap, express_cap);
             while (!express_pending.empty() && (int)g.active.size() < xcap) {
                 size_t need = slot_bytes(h->h_counts[express_pending.front()]);
@@ -511,6 +531,12 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
         if (h->h_counts[c] > 0 && h_phase[c] != OI_PH_DONE) { pending.push_back(c); biggest = std::max(biggest, slot_bytes(h->h_counts[c])); }
     // largest cells first: cost-sorted ragged batches (cost ~ n^3)
     std::stable_sort(pending.begin(), pending.end(), [&](int a, int b) { return h->h_counts[a] > h->h_counts[b]; });
+    if (h->queue.attached()) {
+        // every rank must see the same list: it is built from the same observations and cells in the same order
+        if (pending.size() >= (1u << 24)) return fail(OI_ERR_ARG, "run_lockstep: shared queue holds at most 2^24 - 1 cells");
+        h->queue.begin_run((uint32_t)pending.size());
+        R.q = &h->queue;
+    }
     if (pending.empty()) return OI_OK;
     R.back = pending.size();
     if (max_active <= 0) max_active = 8192;
@@ -634,7 +660,7 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
         if (!any) break;
         if (!progressed) std::this_thread::yield();
     }
-    if (!rc2 && (R.next < R.back || !R.express_pending.empty()))
+    if (!rc2 && (!R.list_empty() || !R.express_pending.empty()))
         rc2 = fail(OI_ERR_NOMEM, "run_lockstep: scratch arena too small for one cell");
     // join: the handle's stream continues after every group
     for (int gi = 0; gi < G; gi++) {
@@ -667,6 +693,7 @@ extern "C" int oi_nlml_grad(oi_handle* h, const double* hypers, int32_t n_hyp, d
     const int nc = (int)h->n_cells;
     std::vector<double> hyp((size_t)nc * 5);
     std::vector<int> phase(nc);
+    h->owned.assign((size_t)nc, 0);
     for (int c = 0; c < nc; c++) {
         for (int q = 0; q < 5; q++) hyp[(size_t)c * 5 + q] = std::exp(hypers[(size_t)c * n_hyp + q]);   // GPR_CS2S3.py:120-122
         phase[c] = h->h_counts[c] > 0 ? OI_PH_EVAL : OI_PH_DONE;
@@ -713,6 +740,8 @@ extern "C" int oi_run(oi_handle* h, const oi_params* p, const double* hypers_in)
     rc.optimiser = p->optimiser == OI_OPT_LBFGS ? 1 : 0;
     for (int q = 0; q < OI_MAXH; q++) rc.x0[q] = p->x0[q];
     std::vector<int> phase(nc);
+    h->owned.assign((size_t)nc, 0);
+    for (int c = 0; c < nc; c++) if (h->h_counts[c] <= 0) h->owned[(size_t)c] = 1;
     // cells without observations: NaN tuple, status NO_OBS (the reference would raise inside pdist)
     std::vector<double> out0((size_t)nc * 8, NAN);
     std::vector<int> st0(nc), nf0(nc, 0);
@@ -753,6 +782,30 @@ extern "C" int oi_get_results(oi_handle* h, double* out, int32_t* n_out, int32_t
     if (nfev_out) CK(cudaMemcpy(nfev_out, h->ca.nfev, nc * 4, cudaMemcpyDeviceToHost));
     if (status_out) CK(cudaMemcpy(status_out, h->ca.status, nc * 4, cudaMemcpyDeviceToHost));
     if (n_out) std::memcpy(n_out, h->h_counts.data(), nc * 4);
+    return OI_OK;
+}
+
+// Several GPU processes of one box share ONE cost-sorted work list (oi_shared_queue.h).  Every process calls this with the
+// same (fresh, unique) POSIX shared-memory name before its first oi_run, and then the same sequence of oi_run calls on the
+// same observations and cells; each cell is computed by exactly one of them.  NULL detaches.
+extern "C" int oi_set_shared_queue(oi_handle* h, const char* shm_name) {
+    if (!h) return fail(OI_ERR_ARG, "oi_set_shared_queue: NULL handle");
+    if (!shm_name) { h->queue.detach(); return OI_OK; }
+    if (std::strlen(shm_name) >= sizeof(h->queue.name) || shm_name[0] != '/') return fail(OI_ERR_ARG, "oi_set_shared_queue: name must start with '/' and be shorter than 128 characters");
+    int e = h->queue.attach(shm_name);
+    if (e) return fail(OI_ERR_STATE, std::string("oi_set_shared_queue: shm_open/mmap failed: ") + std::strerror(e));
+    return OI_OK;
+}
+extern "C" int oi_unlink_shared_queue(const char* shm_name) {
+    if (!shm_name) return fail(OI_ERR_ARG, "oi_unlink_shared_queue: NULL name");
+    OiSharedQueue::unlink_name(shm_name);
+    return OI_OK;
+}
+// owned[n_cells]: 1 where this handle computed the cell in the last oi_run (all cells without a shared queue).
+extern "C" int oi_get_owned(oi_handle* h, uint8_t* owned) {
+    if (!h || !owned) return fail(OI_ERR_ARG, "oi_get_owned: NULL argument");
+    if (!h->have_results) return fail(OI_ERR_STATE, "oi_get_owned: call oi_run first");
+    std::memcpy(owned, h->owned.data(), h->owned.size());
     return OI_OK;
 }
 

@@ -132,6 +132,20 @@ class Handle:
         self._check(self._L.oi_get_results(self._h, _ptr(out), _ptr(n), _ptr(nfev), _ptr(status)))
         return dict(out=out, n=n, nfev=nfev, status=status)
 
+    def set_shared_queue(self, name):
+        """Share one cost-sorted work list with the other GPU processes of the box (same fresh name on every rank, before
+        the first run; None detaches).  See include/oi_b200.h."""
+        self._check(self._L.oi_set_shared_queue(self._h, None if name is None else name.encode()))
+
+    def unlink_shared_queue(self, name):
+        self._L.oi_unlink_shared_queue(name.encode())
+
+    def get_owned(self) -> np.ndarray:
+        """bool mask of the cells this handle computed in the last run."""
+        m = np.zeros(self.n_cells, dtype=np.uint8)
+        self._check(self._L.oi_get_owned(self._h, _ptr(m)))
+        return m.astype(bool)
+
     def debug_trace(self, cell: int, capacity: int = 4096):
         """Record every objective evaluation of one cell's optimiser during the next fits (diagnostic)."""
         self._dbg_cap = int(capacity)

@@ -1,4 +1,5 @@
-"""Cost-balanced assignment of grid cells to GPUs.
+"""Cost-balanced assignment of grid cells to GPUs: a static LPT split (``lpt_partition`` + ``gather_results``) and the
+merge for the dynamic shared work list (``gather_owned``; the list itself lives in csrc/oi_shared_queue.h).
 
 Replaces the reference's round-robin ``split(container, count)`` (GPR_CS2S3.py:18-23, :250-256):
 cells are independent, inputs are replicated on every rank (as in the reference, where every rank
@@ -69,3 +70,33 @@ def gather_results(local_out: np.ndarray, part: np.ndarray, n_cells: int, parts=
         idx = allbuf[r, :k, 0].astype(np.int64)
         full[idx] = allbuf[r, :k, 1:]
     return full
+
+
+def gather_owned(out: np.ndarray, owned: np.ndarray):
+    """Merge for the dynamic mode (``Handle.set_shared_queue``): every rank ran the SAME cells through one shared
+    cost-sorted work list and holds the rows of the cells it computed (``owned``), NaN elsewhere.  One all-gather of the
+    (n_cells, 1 + 8) arrays; each cell's row is taken from the rank that owns it (the lowest such rank: cells without
+    observations are "owned" by every rank).  Returns the full field and the per-rank owned counts."""
+    import torch
+    import torch.distributed as dist
+    out = np.ascontiguousarray(out, dtype=np.float64)
+    owned = np.asarray(owned, dtype=bool)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        if not owned.all():
+            raise ValueError("gather_owned: a single process must own every cell")
+        return out.copy(), np.array([int(owned.sum())])
+    world = dist.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    n, w = out.shape
+    buf = torch.empty((n, w + 1), dtype=torch.float64, device=dev)
+    buf[:, 0] = torch.from_numpy(owned.astype(np.float64)).to(dev)
+    buf[:, 1:] = torch.from_numpy(out).to(dev)
+    allbuf = torch.empty((world, n, w + 1), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(allbuf.view(world * n, w + 1), buf)
+    allbuf = allbuf.cpu().numpy()
+    own = allbuf[:, :, 0] > 0.5                                  # (world, n)
+    if not own.any(axis=0).all():
+        raise RuntimeError(f"gather_owned: {int((~own.any(axis=0)).sum())} cells were computed by no rank")
+    first = np.argmax(own, axis=0)                               # lowest owning rank per cell
+    full = allbuf[first, np.arange(n), 1:]
+    return full, own.sum(axis=1)

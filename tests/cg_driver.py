@@ -8,10 +8,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 def _lib():
     so = os.path.join(_HERE, "_build", "libcg_host.so")
     src = os.path.join(_HERE, "cg_host.cpp")
-    hdrs = [os.path.join(_HERE, "..", "optimalinterpolation_b200", "csrc", h) for h in ("cg_scipy.h", "lbfgs_fast.h")]
+    hdrs = [os.path.join(_HERE, "..", "optimalinterpolation_b200", "csrc", h) for h in ("cg_scipy.h", "lbfgs_fast.h", "oi_shared_queue.h")]
     if (not os.path.exists(so)) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         os.makedirs(os.path.dirname(so), exist_ok=True)
-        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src, "-lrt", "-pthread"])
     L = ctypes.CDLL(so)
     L.cgh_new.restype = ctypes.c_void_p
     L.cgh_free.argtypes = [ctypes.c_void_p]
@@ -24,6 +24,12 @@ def _lib():
     L.cgh_fval.argtypes = [ctypes.c_void_p]; L.cgh_fval.restype = ctypes.c_double
     for nm in ("cgh_status", "cgh_nit", "cgh_nfev"):
         getattr(L, nm).argtypes = [ctypes.c_void_p]; getattr(L, nm).restype = ctypes.c_int
+    L.sq_new.restype = ctypes.c_void_p
+    L.sq_free.argtypes = [ctypes.c_void_p]
+    L.sq_attach.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    L.sq_unlink.argtypes = [ctypes.c_char_p]
+    L.sq_begin.argtypes = [ctypes.c_void_p, ctypes.c_uint]
+    L.sq_take.argtypes = [ctypes.c_void_p, ctypes.c_int]; L.sq_take.restype = ctypes.c_long
     L.lbh_new.restype = ctypes.c_void_p
     L.lbh_free.argtypes = [ctypes.c_void_p]
     L.lbh_init.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double]

@@ -37,3 +37,19 @@ extern "C" void cgh_dcstep(double* v, int* brackt, double fp, double dp, double 
     // v = {stx, fx, dx, sty, fy, dy, stp}
     oicg::dcstep(v[0], v[1], v[2], v[3], v[4], v[5], v[6], fp, dp, *brackt, stpmin, stpmax);
 }
+// the work list shared by the GPU processes of a box (csrc/oi_shared_queue.h): host access for the multi-process CPU test
+#include "../optimalinterpolation_b200/csrc/oi_shared_queue.h"
+extern "C" {
+OiSharedQueue* sq_new() { return new OiSharedQueue(); }
+void sq_free(OiSharedQueue* q) { q->detach(); delete q; }
+int sq_attach(OiSharedQueue* q, const char* name) { return q->attach(name); }
+void sq_unlink(const char* name) { OiSharedQueue::unlink_name(name); }
+void sq_begin(OiSharedQueue* q, unsigned n) { q->begin_run(n); }
+long sq_take(OiSharedQueue* q, int small_end) {       // peek + claim until it succeeds or the list is empty
+    for (;;) {
+        long i = small_end ? q->peek_back() : q->peek_front();
+        if (i < 0) return -1;
+        if (small_end ? q->claim_back(i) : q->claim_front(i)) return i;
+    }
+}
+}

@@ -192,3 +192,41 @@ def test_two_handles_in_one_process(small_day):
     h0.close(); h1.close()
     print("second handle on", second)
     assert np.array_equal(outs[0], outs[1], equal_nan=True) and np.isfinite(outs[0][:, 0]).mean() > 0.8
+
+
+def test_shared_work_list_two_handles(small_day):
+    """Two handles (two host threads, as two GPU processes would) draw from ONE shared cost-sorted work list
+    (oi_set_shared_queue): every cell is computed by exactly one of them and the merged field is bit-identical to a
+    single handle's (a cell's numbers do not depend on who computes it)."""
+    import threading
+    import optimalinterpolation_b200 as oi
+    d = small_day
+    cells = np.arange(0, len(d.X), 3)
+    X = d.X[cells]
+    ref_h = oi.Handle(0)
+    p = ref_h.make_params(d.radius_km * 1000.0, d.T_mid, d.mean, d.x0, mode=0)
+    ref = ref_h.gpr_day(d.x_train, d.y_train, d.t_train, d.z, X, p)
+    assert ref_h.get_owned().all()
+    ref_h.close()
+    name = f"/oi_b200_gputest_{os.getpid()}"
+    hs = [oi.Handle(0), oi.Handle(0)]
+    for h in hs:
+        h.set_shared_queue(name)
+    outs = [None, None]
+
+    def work(k):
+        for _ in range(2):                                   # two consecutive runs: the list's generation advances on both
+            r = hs[k].gpr_day(d.x_train, d.y_train, d.t_train, d.z, X, p)
+        outs[k] = (r, hs[k].get_owned())
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    [t.start() for t in th]; [t.join() for t in th]
+    (r0, o0), (r1, o1) = outs
+    empty = r0["n"] == 0
+    assert np.array_equal(o0 & o1, empty)                    # only cells without observations are "owned" by both
+    assert (o0 | o1).all() and o0.sum() > len(cells) // 10 and o1.sum() > len(cells) // 10
+    merged = np.where(o0[:, None], r0["out"], r1["out"])
+    assert np.array_equal(merged, ref["out"], equal_nan=True)
+    assert np.array_equal(np.where(o0, r0["nfev"], r1["nfev"]), ref["nfev"])
+    hs[0].set_shared_queue(None); hs[1].set_shared_queue(None)
+    hs[0].unlink_shared_queue(name)
+    [h.close() for h in hs]
