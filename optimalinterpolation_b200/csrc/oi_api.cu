@@ -372,7 +372,12 @@ struct LockstepRun {
         const int cap = is_express(gi) ? std::min(express_cap, g.slot_cap) : g.slot_cap;
         if (!is_express(gi)) {
             const bool small_end = takes_small(gi);
-            while ((int)g.active.size() < cap) {
+            // From a list shared with other ranks a group claims at most 64 cells per iteration: batches then grow over a few
+            // (short) iterations instead of one rank taking a sixth of the list in its first call, and a rank whose batches
+            // are large iterates -- and therefore claims -- more slowly: the ranks' shares balance themselves.
+            int claimed = 0;
+            const int claim_cap = q ? 64 : 0x7fffffff;
+            while ((int)g.active.size() < cap && claimed < claim_cap) {
                 const long idx = peek(small_end);
                 if (idx < 0) break;
                 const int c = pending[(size_t)idx];
@@ -380,7 +385,7 @@ struct LockstepRun {
                 if (g.used + need > g.arena_bytes) break;
                 if (!g.active.empty() && g.tiles + cell_tiles(c) > tile_budget) break;   // enough work to fill the GPU share
                 if (!claim(small_end, idx)) continue;                                     // another rank was faster: look again
-                g.used += need; g.tiles += cell_tiles(c); g.active.push_back(c);
+                g.used += need; g.tiles += cell_tiles(c); g.active.push_back(c); claimed++;
                 h->owned[(size_t)c] = 1;
             }
         }
