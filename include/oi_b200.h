@@ -107,8 +107,9 @@ int  oi_sizeof_stats(void);
 const char* oi_last_error(void);
 
 int  oi_create(int device, oi_handle** out);
-/* Launch on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g. torch's current stream, so
- * that the caller's CUDA events bracket the kernels.  NULL restores the handle's own stream. */
+/* Launch on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g. a torch.cuda.Stream, so that the caller's
+ * CUDA events bracket the kernels.  NULL (0) restores the handle's own stream: the legacy default stream (whose handle is
+ * 0) cannot be selected -- pass a stream you created (bench.py does). */
 int  oi_set_stream(oi_handle* h, void* cuda_stream);
 void oi_destroy(oi_handle* h);
 

@@ -35,6 +35,7 @@ struct oi_handle {
     // observations
     double *ox = nullptr, *oy = nullptr, *ot = nullptr, *oz = nullptr;
     int64_t n_obs = 0, obs_cap = 0;
+    std::vector<double> h_t;            // host copy of t: the day window's index ranges are found on the host
     double t_lo = -INFINITY, t_hi = INFINITY, t_shift = 0.0;      // day window of the gather (oi_set_time_window)
     // cells
     double* X = nullptr;
@@ -156,6 +157,7 @@ extern "C" int oi_set_observations(oi_handle* h, const double* x, const double* 
         h->obs_cap = n_obs;
     }
     h->n_obs = n_obs;
+    h->h_t.assign(t, t + n_obs);
     CK(cudaMemcpyAsync(h->ox, x, n_obs * 8, cudaMemcpyHostToDevice, h->st));
     CK(cudaMemcpyAsync(h->oy, y, n_obs * 8, cudaMemcpyHostToDevice, h->st));
     CK(cudaMemcpyAsync(h->ot, t, n_obs * 8, cudaMemcpyHostToDevice, h->st));
@@ -198,8 +200,24 @@ extern "C" int oi_gather_neighbours(oi_handle* h, double radius_m, int32_t* coun
     CK(cudaSetDevice(h->device));
     const double r2 = radius_m * radius_m;
     const int nc = (int)h->n_cells, no = (int)h->n_obs;
+    // Maximal runs of observations inside the day window (a resident season is stream-major / day-major: one run per
+    // stream; 20x less to scan than the season for a 180-day season).  More than OI_MAX_RANGES runs: scan everything.
+    OiRanges rg; rg.n = 1; rg.lo[0] = 0; rg.hi[0] = no;
+    if (std::isfinite(h->t_lo) || std::isfinite(h->t_hi)) {
+        OiRanges w; w.n = 0;
+        bool ok = true;
+        for (int i = 0; i < no && ok;) {
+            if (!(h->h_t[i] >= h->t_lo && h->h_t[i] <= h->t_hi)) { i++; continue; }
+            int j = i;
+            while (j < no && h->h_t[j] >= h->t_lo && h->h_t[j] <= h->t_hi) j++;
+            if (w.n == OI_MAX_RANGES) { ok = false; break; }
+            w.lo[w.n] = i; w.hi[w.n] = j; w.n++;
+            i = j;
+        }
+        if (ok) rg = w;
+    }
     CK(cudaEventRecord(h->ev[8], h->st));
-    oi_launch_count(h->ox, h->oy, h->ot, no, h->X, nc, r2, h->t_lo, h->t_hi, h->counts, h->st);
+    oi_launch_count(h->ox, h->oy, h->ot, no, h->X, nc, r2, h->t_lo, h->t_hi, rg, h->counts, h->st);
     oi_launch_scan(h->counts, nc, h->offsets, h->st);
     CK(cudaGetLastError());
     long long total = 0;
@@ -217,7 +235,7 @@ extern "C" int oi_gather_neighbours(oi_handle* h, double radius_m, int32_t* coun
     h->total = total;
     h->h_offsets.assign((size_t)nc + 1, 0);
     for (int c = 0; c < nc; c++) h->h_offsets[c + 1] = h->h_offsets[c] + h->h_counts[c];
-    if (total > 0) oi_launch_fill(h->ox, h->oy, h->ot, no, h->X, nc, r2, h->t_lo, h->t_hi, h->offsets, h->indices, h->st);
+    if (total > 0) oi_launch_fill(h->ox, h->oy, h->ot, no, h->X, nc, r2, h->t_lo, h->t_hi, rg, h->offsets, h->indices, h->st);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[9], h->st));
     CK(cudaStreamSynchronize(h->st));

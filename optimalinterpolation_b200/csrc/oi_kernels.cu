@@ -20,7 +20,7 @@ template <bool FILL>
 __global__ void __launch_bounds__(256) k_gather(const double* __restrict__ ox, const double* __restrict__ oy,
                                                 const double* __restrict__ ot, int n_obs,
                                                 const double* __restrict__ X, int n_cells, double r2, double t_lo, double t_hi,
-                                                int* __restrict__ counts, const long long* __restrict__ offsets,
+                                                OiRanges rg, int* __restrict__ counts, const long long* __restrict__ offsets,
                                                 int* __restrict__ indices) {
     __shared__ double sx[G_CHUNK], sy[G_CHUNK], st[G_CHUNK];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -31,8 +31,11 @@ __global__ void __launch_bounds__(256) k_gather(const double* __restrict__ ox, c
     long long base = 0;
     if (FILL && live) base = offsets[cell];
     int cnt = 0;
-    for (int c0 = 0; c0 < n_obs; c0 += G_CHUNK) {
-        int m = min(G_CHUNK, n_obs - c0);
+    // Only the index ranges that can hold observations of the day window are scanned (ascending, so the neighbour order
+    // is unchanged): a resident season is stream-major / day-major, i.e. one contiguous range per stream.
+    for (int ri = 0; ri < rg.n; ri++)
+    for (int c0 = rg.lo[ri]; c0 < rg.hi[ri]; c0 += G_CHUNK) {
+        int m = min(G_CHUNK, rg.hi[ri] - c0);
         __syncthreads();
         for (int q = threadIdx.x; q < m; q += 256) { sx[q] = ox[c0 + q]; sy[q] = oy[c0 + q]; st[q] = ot[c0 + q]; }
         __syncthreads();
@@ -195,15 +198,15 @@ static_assert(OI_SMEM_PIPE == PIPE_BYTES, "pipeline size");
 static_assert(PIPE_BYTES >= NB * TS * 8 + 4 * 64 * 8 + 16, "packed diagonal block must fit the pipeline buffers");
 
 void oi_launch_count(const double* ox, const double* oy, const double* ot, int n_obs, const double* X, int n_cells, double r2,
-                     double t_lo, double t_hi, int* counts, cudaStream_t st) {
-    k_gather<false><<<(n_cells + 7) / 8, 256, 0, st>>>(ox, oy, ot, n_obs, X, n_cells, r2, t_lo, t_hi, counts, nullptr, nullptr);
+                     double t_lo, double t_hi, const OiRanges& rg, int* counts, cudaStream_t st) {
+    k_gather<false><<<(n_cells + 7) / 8, 256, 0, st>>>(ox, oy, ot, n_obs, X, n_cells, r2, t_lo, t_hi, rg, counts, nullptr, nullptr);
 }
 void oi_launch_scan(const int* counts, int n, long long* offsets, cudaStream_t st) {
     k_scan_counts<<<1, 1024, 0, st>>>(counts, n, offsets);
 }
 void oi_launch_fill(const double* ox, const double* oy, const double* ot, int n_obs, const double* X, int n_cells, double r2,
-                    double t_lo, double t_hi, const long long* offsets, int* indices, cudaStream_t st) {
-    k_gather<true><<<(n_cells + 7) / 8, 256, 0, st>>>(ox, oy, ot, n_obs, X, n_cells, r2, t_lo, t_hi, nullptr, offsets, indices);
+                    double t_lo, double t_hi, const OiRanges& rg, const long long* offsets, int* indices, cudaStream_t st) {
+    k_gather<true><<<(n_cells + 7) / 8, 256, 0, st>>>(ox, oy, ot, n_obs, X, n_cells, r2, t_lo, t_hi, rg, nullptr, offsets, indices);
 }
 void oi_launch_pack(const int* indices, long long total, const double* ox, const double* oy, const double* ot,
                     const double* oz, double mean, double t_shift, double* px, double* py, double* pt, double* pr, cudaStream_t st) {

@@ -16,11 +16,14 @@ struct OiRunConst {
     int n_hyp, grad_convention, maxiter, optimiser;
     double x0[6];
 };
+// index ranges [lo, hi) of the observation arrays that the neighbour gather scans (ascending, disjoint)
+#define OI_MAX_RANGES 16
+struct OiRanges { int n; int lo[OI_MAX_RANGES], hi[OI_MAX_RANGES]; };
 void oi_launch_count(const double* ox, const double* oy, const double* ot, int n_obs, const double* X, int n_cells, double r2,
-                     double t_lo, double t_hi, int* counts, cudaStream_t st);
+                     double t_lo, double t_hi, const OiRanges& rg, int* counts, cudaStream_t st);
 void oi_launch_scan(const int* counts, int n, long long* offsets, cudaStream_t st);
 void oi_launch_fill(const double* ox, const double* oy, const double* ot, int n_obs, const double* X, int n_cells, double r2,
-                    double t_lo, double t_hi, const long long* offsets, int* indices, cudaStream_t st);
+                    double t_lo, double t_hi, const OiRanges& rg, const long long* offsets, int* indices, cudaStream_t st);
 void oi_launch_pack(const int* indices, long long total, const double* ox, const double* oy, const double* ot,
                     const double* oz, double mean, double t_shift, double* px, double* py, double* pt, double* pr, cudaStream_t st);
 void oi_launch_build(const OiSlot* slots, int A, int Nmax, const int* cnt_gt, OiCellArrays ca, OiPacked pk, cudaStream_t st);

@@ -56,7 +56,8 @@ class Handle:
             pass
 
     def set_stream(self, cuda_stream_ptr):
-        """Launch on a caller-owned stream (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
+        """Launch on a caller-owned stream (``torch.cuda.Stream().cuda_stream``).  0 / None restores the handle's own
+        stream: torch's legacy default stream has the handle 0 and therefore cannot be selected."""
         self._check(self._L.oi_set_stream(self._h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
 
     def set_observations(self, x, y, t, z):
