@@ -20,10 +20,6 @@ print("TFLOP/s overall", st["flops"] / st["ms_total"] * 1e-9, "factor kernels", 
 for k in ("chol", "trtri", "lauum"):
     if st["ms_" + k] > 0:
         print(k, "TFLOP/s", st["flops_" + k] / st["ms_" + k] * 1e-9, "ms", st["ms_" + k])
-if st["launches_persistent"]:
-    cyc = st["cycles_phase"]; tot = sum(cyc) or 1
-    print("persistent launches", st["launches_persistent"], "phase shares (build, chol, scale, fwd+trtri, alpha, lauum, finalize, idle):",
-          [round(c / tot, 3) for c in cyc])
 print("graph captures", st["n_graph_captures"], "graph launches", st["n_graph_launches"], "ms_graph", round(st["ms_graph"], 1))
 print("express cells", st["n_express_cells"], "iterations", st["n_iterations"], "launches", st["n_launches"])
 print("nfev mean", res["nfev"].mean(), "max", res["nfev"].max(), "status hist", np.bincount(res["status"]))

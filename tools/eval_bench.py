@@ -26,10 +26,7 @@ for r in range(reps):
     t0 = time.perf_counter(); f, g = h.nlml_grad(hyp, d.mean); walls.append((time.perf_counter() - t0) * 1e3)
     st = h.stats()
 print("wall ms per evaluation of all cells (incl. H2D/D2H of hypers and results):", [round(w, 2) for w in walls],
-      " => TFLOP/s (best)", st["flops"] / min(walls) * 1e-9, "groups", st["n_groups"], "group_size", st["group_size"])
-if st["launches_persistent"]:
-    cyc = st["cycles_phase"]; tot = sum(cyc) or 1
-    print("  persistent phase shares (build, chol, scale, fwd+trtri, alpha, lauum, finalize, idle):", [round(c / tot, 3) for c in cyc])
+      " => TFLOP/s (best)", st["flops"] / min(walls) * 1e-9, "groups", st["n_groups"])
 tot = sum(st[k] for k in st if k.startswith("ms_") and k not in ("ms_total", "ms_gather", "ms_factor", "ms_persistent"))
 print("cells", len(cells), "sum ms", round(tot, 3), "checksum", float(np.nansum(f)), float(np.nansum(g)))
 for k in ("build", "chol", "fwd", "trtri", "alpha", "lauum", "finalize"):
