@@ -15,7 +15,7 @@ There is ONE timed loop of exactly --steps steps (after --warmup identical steps
   value : the same steps with the host<->device copies taken out: per step, the device time the library measures with
           CUDA events on its launching stream from the first gather kernel to the last result (oi_stats.ms_gather +
           ms_total; max over ranks per step)
-After the loop, while the wall-clock budget (--budget-s, default 520 s from process start) allows and only at N=1:
+After the loop, while the wall-clock budget (--budget-s, default 575 s from process start) allows and only at N=1:
 the CPU baseline sample, a single-stream pass that times each kernel family, and the WHOLE day in one call
 (BASELINE.json configs[1]; ~8 steps' worth, reported under "full_day").
 
@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--sharding", default="dynamic", choices=["dynamic", "lpt"],
                     help="N>1: dynamic = one cost-sorted work list shared by the ranks (POSIX shared memory), lpt = static LPT split on n^3")
     ap.add_argument("--max-active", type=int, default=0)
-    ap.add_argument("--budget-s", type=float, default=float(os.environ.get("OI_BENCH_BUDGET_S", 520)),
+    ap.add_argument("--budget-s", type=float, default=float(os.environ.get("OI_BENCH_BUDGET_S", 575)),
                     help="wall-clock budget of the whole run; the optional passes after the timed loop only start while it allows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-day", action="store_true", help="skip the single whole-day pass (N=1 only)")
