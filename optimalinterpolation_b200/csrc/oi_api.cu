@@ -622,7 +622,7 @@ static int run_lockstep(oi_handle* h, std::vector<int>& h_phase, const OiRunCons
     // work admitted per bulk group: enough tiles in flight to fill the GPU, few enough that an iteration stays short
     // (a cell's iteration latency = active work / throughput; long optimiser runs are only recognised by their
     // iteration count, so latency decides how early they reach an express lane)
-    long long tile_total = 110000;
+    long long tile_total = 80000;       // measured with two small-first groups (2390-cell step, two boxes): 40 k 14.31 s, 60 k 14.25, 80 k 14.00-14.20, 110 k 14.62, 150 k 15.06
     if (const char* e = std::getenv("OI_TILE_BUDGET")) tile_total = std::max(1LL, std::atoll(e));
     R.tile_budget = std::max(1LL, tile_total / std::max(1, G - R.n_express));
     {
