@@ -226,7 +226,7 @@ def test_shared_work_list_two_handles(small_day):
     empty = r0["n"] == 0
     assert np.array_equal(o0 & o1, empty)                    # only cells without observations are "owned" by both
     print("cells owned by the two handles:", int(o0.sum()), int(o1.sum()), "of", len(cells))
-    assert (o0 | o1).all() and o0.sum() > empty.sum() and o1.sum() > empty.sum()
+    assert (o0 | o1).all()          # (how the cells split between the two depends on thread timing: not asserted)
     merged = np.where(o0[:, None], r0["out"], r1["out"])
     assert np.array_equal(merged, ref["out"], equal_nan=True)
     assert np.array_equal(np.where(o0, r0["nfev"], r1["nfev"]), ref["nfev"])
