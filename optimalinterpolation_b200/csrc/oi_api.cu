@@ -220,11 +220,12 @@ extern "C" int oi_gather_neighbours(oi_handle* h, double radius_m, int32_t* coun
     oi_launch_count(h->ox, h->oy, h->ot, no, h->X, nc, r2, h->t_lo, h->t_hi, rg, h->counts, h->st);
     oi_launch_scan(h->counts, nc, h->offsets, h->st);
     CK(cudaGetLastError());
-    long long total = 0;
-    CK(cudaMemcpyAsync(&total, h->offsets + nc, 8, cudaMemcpyDeviceToHost, h->st));
     h->h_counts.resize(nc);
+    h->h_offsets.resize((size_t)nc + 1);
     CK(cudaMemcpyAsync(h->h_counts.data(), h->counts, (size_t)nc * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(h->h_offsets.data(), h->offsets, ((size_t)nc + 1) * 8, cudaMemcpyDeviceToHost, h->st));   // the device scan's result
     CK(cudaStreamSynchronize(h->st));
+    const long long total = h->h_offsets[(size_t)nc];
     if (total > h->idx_cap) {
         cudaFree(h->indices); cudaFree(h->px); cudaFree(h->py); cudaFree(h->pt); cudaFree(h->pr);
         size_t c = (size_t)std::max<long long>(total, 1);
@@ -233,8 +234,6 @@ extern "C" int oi_gather_neighbours(oi_handle* h, double radius_m, int32_t* coun
         h->idx_cap = total;
     }
     h->total = total;
-    h->h_offsets.assign((size_t)nc + 1, 0);
-    for (int c = 0; c < nc; c++) h->h_offsets[c + 1] = h->h_offsets[c] + h->h_counts[c];
     if (total > 0) oi_launch_fill(h->ox, h->oy, h->ot, no, h->X, nc, r2, h->t_lo, h->t_hi, rg, h->offsets, h->indices, h->st);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[9], h->st));

@@ -177,6 +177,11 @@ def test_fit_matches_oracle(small_day):
     print(f"small-day fit parity over {N} cells: reference sorted-vs-tree {summary(floor)}\n GPU vs tree {summary(gpu)}\n"
           f" miss rate GPU {miss_gpu:.4f} reference floor {miss_floor:.4f} sigma {sigma:.4f}; nfev mean GPU {res['nfev'].mean():.1f} "
           f"ref {fx['nfev_tree'].mean():.1f}")
+    import json
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    json.dump(dict(cells=int(N), reference_sorted_vs_tree=summary(floor), gpu_vs_tree=summary(gpu)),
+              open(os.path.join(out_dir, "parity_small_day.json"), "w"), indent=1)
     assert miss_gpu <= miss_floor + 0.001 + 2 * sigma
     assert np.nanmedian(gpu["dfs"]) < 1e-3          # and the typical cell agrees to round-off
 
