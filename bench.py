@@ -130,7 +130,10 @@ def make_config(args, world, day, cells, counts_step):
     return {"workload": wl, "cells_per_step": int(len(cells)), "n_obs": int(day.z.size),
             "n_min_median_max": [int(counts_step.min()), int(np.median(counts_step)), int(counts_step.max())],
             "optimiser": opt,
-            "sharding": f"LPT on n^3 over {world} ranks, imbalance {imbalance(counts_step, parts):.4f}",
+            "sharding": (f"dynamic: one cost-sorted work list shared by the {world} ranks (largest cells claimed from the front, smallest "
+                         f"from the back; 64-bit cursor word in POSIX shared memory), every rank holds all {len(cells)} cells")
+            if world > 1 and args.sharding == "dynamic" else
+            f"LPT on n^3 over {world} ranks, imbalance {imbalance(counts_step, parts):.4f}",
             "cache": "per-iteration working set (sum of n_pad^2*8 B over active cells, GBs) is far larger than the 126 MB L2; no L2 flush needed"}, parts
 
 
@@ -245,8 +248,6 @@ def main():
         h.set_shared_queue(name[0])
         dist.barrier()
         mine = np.arange(len(cells))
-        config["sharding"] = (f"dynamic: one cost-sorted work list shared by the {world} ranks (largest cells claimed from the front, smallest "
-                              f"from the back; 64-bit cursor word in POSIX shared memory), every rank holds all {len(cells)} cells")
     else:
         mine = parts[rank]
     Xmine = pinned(Xstep[mine])
