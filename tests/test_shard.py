@@ -56,7 +56,7 @@ def test_gather_world2_gloo():
     assert np.array_equal(full[ok, 0], np.arange(37)[ok] * 1.0) and np.allclose(full[ok, 7], np.arange(37)[ok] + 1.75)
 
 
-def _queue_worker(rank, name, n_items, n_runs, q):
+def _queue_worker(rank, name, n_items, n_runs, q, barrier):
     import time
     import cg_driver
     L = cg_driver._lib()
@@ -65,6 +65,7 @@ def _queue_worker(rank, name, n_items, n_runs, q):
     rng = np.random.default_rng(rank)
     taken = []
     for run in range(n_runs):
+        barrier.wait()                                             # the collective that ends every step of a real job
         L.sq_begin(sq, n_items[run])
         mine = []
         while True:
@@ -72,7 +73,7 @@ def _queue_worker(rank, name, n_items, n_runs, q):
             if i < 0:
                 break
             mine.append(int(i))
-            if rng.uniform() < 0.02:
+            if rng.uniform() < 0.05:
                 time.sleep(0.0005)
         taken.append(mine)
         time.sleep(0.01 * rank)                                    # ranks leave a run at different times
@@ -90,7 +91,8 @@ def test_shared_work_list_every_cell_claimed_exactly_once():
     n_items = [5000, 1, 1237]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_queue_worker, args=(r, name, n_items, len(n_items), q)) for r in range(4)]
+    barrier = ctx.Barrier(4)
+    procs = [ctx.Process(target=_queue_worker, args=(r, name, n_items, len(n_items), q, barrier)) for r in range(4)]
     [p.start() for p in procs]
     got = dict(q.get(timeout=120) for _ in range(4))
     [p.join(60) for p in procs]
