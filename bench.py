@@ -245,8 +245,19 @@ def main():
         # fresh segment name on every rank, attached before the first run
         name = [f"/oi_b200_bench_{os.getpid()}_{int(time.time())}"]
         dist.broadcast_object_list(name, src=0)
-        h.set_shared_queue(name[0])
-        dist.barrier()
+        ok = torch.ones(1, device=dev)
+        try:
+            h.set_shared_queue(name[0])
+        except Exception as e:                       # no POSIX shared memory in this container: every rank falls back together
+            print(f"rank {rank}: shared work list unavailable ({e}); static LPT split instead", file=sys.stderr)
+            ok[0] = 0
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok[0]) < 0.5:
+            h.set_shared_queue(None)
+            dynamic = False
+            from optimalinterpolation_b200.shard import imbalance
+            config["sharding"] = f"LPT on n^3 over {world} ranks, imbalance {imbalance(counts_step, parts):.4f} (shared memory unavailable: fell back from the dynamic list)"
+    if dynamic:
         mine = np.arange(len(cells))
     else:
         mine = parts[rank]
