@@ -9,16 +9,16 @@ for n in ("parity_1k.json", "parity_lbfgs_1k.json", "parity_cfg5.json", "parity_
 
 
 def row(name, fl, gp):
-    f = lambda s: (f"gate met by {100 * s['frac_gate']:.2f} % of {s['cells']} cells (|Δfs| ≤ 1 mm: {100 * s['frac_fs_1mm']:.2f} %, NLML rule: "
+    f = lambda s: (f"gate met by {100 * s['frac_gate']:.2f} % of {s['cells']} cells (abs Δfs ≤ 1 mm: {100 * s['frac_fs_1mm']:.2f} %, NLML rule: "
                    f"{100 * s['frac_nlml']:.2f} %; NaN only on one side: {s['nan_only_candidate'] + s['nan_only_reference']}, NaN on both: {s['nan_both']}; "
-                   f"|Δfs| median {s['dfs_mm_median']:.1e} mm, p99 {s['dfs_mm_p99']:.2g} mm)")
+                   f"abs Δfs median {s['dfs_mm_median']:.1e} mm, p99 {s['dfs_mm_p99']:.2g} mm)")
     return f"| {name} | {f(fl)} | {f(gp)} |"
 
 
 table = "\n".join([
     row(f"full day, {p1k['cells']} cells, n = {p1k['n_min']}…{p1k['n_max']} ({100 * p1k['frac_cells_n_gt_1100']:.0f} % with n > 1100)", p1k["reference_sorted_vs_tree"], p1k["gpu_vs_tree"]),
     row(f"small day, {ps['cells']} cells, n = 40…300", ps["reference_sorted_vs_tree"], ps["gpu_vs_tree"]),
-    f"| config 5 (12.5 km / 500 km), {pc['cells']} cells, n = {min(pc['n'])}…{max(pc['n'])} | (one order only) | gate met by {pc['cells'] - int(round((1 - pc['frac_gate']) * pc['cells']))} of {pc['cells']}; |Δfs| max {pc['dfs_mm_max']:.1e} mm, likelihood within {max(abs(v) for v in pc['rel_lZ'] if v is not None):.0e} relative |"])
+    f"| config 5 (12.5 km / 500 km), {pc['cells']} cells, n = {min(pc['n'])}…{max(pc['n'])} | (one order only) | gate met by {pc['cells'] - int(round((1 - pc['frac_gate']) * pc['cells']))} of {pc['cells']}; abs Δfs max {pc['dfs_mm_max']:.1e} mm, likelihood within {max(abs(v) for v in pc['rel_lZ'] if v is not None):.0e} relative |"])
 fl, gp = p1k["reference_sorted_vs_tree"], p1k["gpu_vs_tree"]
 numbers = (f"`profiles/r02_parity_*.json`; the reference misses its own gate on {100 * (1 - fl['frac_gate']):.1f} % of the full-day cells, the CUDA path "
            f"misses the reference on {100 * (1 - gp['frac_gate']):.1f} %")
