@@ -15,6 +15,11 @@
  *   GPR3D(index, opt=True)     (:143-168, :173-184)    oi_run(OI_MODE_FIT) / oi_gpr_day()
  *   GPR3D(index, opt=False)    (:169-172, :185-186)    oi_run(OI_MODE_PREDICT) with hypers_in
  *   results tuple (:184)                               out[n_cells][8] = fs, sfs2(std), lZ, lx, ly, lt, sf2, sn2
+ *   scipy.optimize.minimize(method='CG') (:166)        oi_params.optimiser = OI_OPT_CG (restated evaluation by evaluation);
+ *                                                      OI_OPT_LBFGS = the fast mode (not the reference's stopping points)
+ *   split(container, count) + COMM.scatter (:18-23,    one process per GPU: a static split on the host (shard.py) or
+ *     :250-256), COMM.gather (:262)                    oi_set_shared_queue() / oi_get_owned(): one cost-sorted work list
+ *                                                      shared by the processes of a box; the gather stays with the host (NCCL)
  *
  * Conventions: all pointers are HOST pointers to C-contiguous arrays; the library owns every
  * device allocation behind the opaque handle.  One handle per GPU; a handle is not thread-safe;
@@ -40,10 +45,9 @@ enum { OI_OK = 0, OI_ERR_ARG = -1, OI_ERR_CUDA = -2, OI_ERR_STATE = -3, OI_ERR_N
 /* mode */
 enum { OI_MODE_FIT = 0,      /* GPR3D(index, opt=True):  fit by CG then predict  */
        OI_MODE_PREDICT = 1   /* GPR3D(index, opt=False): predict with hypers_in   */ };
-/* execution engine.  LOCKSTEP (default): one launch per algorithmic step over all active cells, n_groups
- * independent groups on their own streams.  PERSISTENT: one resident kernel, groups of CTAs walk cells through
- * whole evaluations + optimiser steps (measured slower on the day workload; kept as an option).
- * Both run the same tile code and give bit-identical results. */
+/* execution engine.  LOCKSTEP: one launch per algorithmic step over all active cells, n_groups independent groups on
+ * their own streams.  The experimental PERSISTENT engine of v1.1 (one resident kernel with a global-memory barrier;
+ * measured slower, never race-checked) was removed in v1.2: oi_run refuses it. */
 enum { OI_ENGINE_LOCKSTEP = 0, OI_ENGINE_PERSISTENT = 1 };
 /* gradient convention of SMLII: the reference's components 3 and 4 are twice the true derivative
  * (GPR_CS2S3.py:135-138).  REFERENCE reproduces that; EXACT gives the true gradient. */
@@ -71,9 +75,9 @@ typedef struct oi_params {
     double scratch_gib;     /* device scratch budget for the lockstep batch, 0 => automatic             */
     int32_t max_active;     /* maximum cells evaluated per lockstep iteration, 0 => automatic           */
     int32_t n_groups;       /* lockstep engine: independent groups (one CUDA stream each) whose kernels overlap, 0 => automatic */
-    int32_t engine;         /* OI_ENGINE_*                                                                */
-    int32_t group_size;     /* persistent engine: CTAs that share one cell, 0 => automatic (4, growing in the tail) */
-    int32_t evals_per_launch; /* persistent engine: evaluations a cell advances per launch, 0 => 128      */
+    int32_t engine;         /* must be OI_ENGINE_LOCKSTEP (0)                                              */
+    int32_t group_size;     /* unused (was: persistent engine, removed in v1.2); kept for the struct layout */
+    int32_t evals_per_launch; /* unused (same)                                                              */
     int32_t optimiser;      /* OI_OPT_*: 0 = the reference's scipy CG (parity mode), 1 = exact-gradient L-BFGS (fast mode) */
 } oi_params;
 
@@ -91,14 +95,13 @@ typedef struct oi_stats {
     double flops_chol, flops_trtri, flops_lauum;   /* n^3/3 each per evaluation            */
     int64_t launches_chol, launches_trtri, launches_lauum;
     int64_t n_groups;       /* groups used (last launch); lockstep engine with > 1: the per-family ms_* are per-stream times that overlap */
-    int64_t group_size;     /* persistent engine: CTAs per group of the last launch                      */
-    int64_t launches_persistent;
+    int64_t group_size;     /* unused since v1.2 (layout kept)                                            */
+    int64_t launches_persistent; /* unused since v1.2                                                     */
     int64_t n_graph_captures, n_graph_launches; /* lockstep engine: small-batch iterations replayed as CUDA graphs */
     double ms_graph;        /* device time of those iterations (not split by kernel family)              */
     int64_t n_express_cells; /* lockstep engine: cells handed to the express lanes (long optimiser runs)           */
-    double ms_persistent;   /* device time inside k_gp_persistent (CUDA events)                          */
-    double cycles_phase[8]; /* persistent engine: CTA clock cycles per phase summed over CTAs:
-                               build, chol, scale, fwd+trtri, alpha, lauum+trace, finalize, idle/queue   */
+    double ms_persistent;   /* unused since v1.2                                                         */
+    double cycles_phase[8]; /* unused since v1.2                                                         */
 } oi_stats;
 
 int  oi_version(void);
