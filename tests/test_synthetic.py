@@ -29,3 +29,37 @@ def test_full_day_shape():
     assert len(d.X) == 19109 and d.T == 9 and d.T_mid == 4 and len(d.x0) == 6
     assert np.all(d.x_train % 25000.0 == 0) and np.all(d.z >= -0.37) and np.all(d.z <= 0.63)
     assert d.z.size == 38144
+
+
+def test_cfg5_day_geometry():
+    """BASELINE.json configs[4]: 12.5 km lattice, 500 km radius -- thousands of observations per cell."""
+    from scipy.spatial import cKDTree
+    from optimalinterpolation_b200.synthetic import make_day_cfg5
+    d = make_day_cfg5()
+    assert d.shape == (640, 640) and d.grid_res_km == 12.5 and d.radius_km == 500.0 and len(d.X) == 76425
+    assert np.allclose(d.x0[:2], np.log(12500.0))                      # x0 follows grid_res (GPR_CS2S3.py:217)
+    cnt = np.asarray(cKDTree(np.c_[d.x_train, d.y_train]).query_ball_point(d.X[::256], r=500e3, return_length=True))
+    assert 1000 < cnt.min() and 3000 < np.median(cnt) < 4200 and cnt.max() < 6000
+
+
+def test_bench_config_is_one_object_for_both_arms():
+    """bench.py builds `config` in one function from the workload alone, so the reference arm's line carries the GPU
+    arm's config (the driver compares them) at every N."""
+    import importlib.util, os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(b)
+        args = b.parse()
+    finally:
+        sys.argv = argv
+    for world in (1, 8):
+        day, cells = b.make_workload(args, world)
+        counts = np.arange(len(cells)) % 1500 + 200
+        c1, parts = b.make_config(args, world, day, cells, counts)
+        c2, _ = b.make_config(args, world, day, cells, counts)
+        assert c1 == c2 and c1["cells_per_step"] == len(cells) and sum(len(p) for p in parts) == len(cells)
+        assert ("dynamic" in c1["sharding"]) == (world > 1)
+    assert len(b.make_workload(args, 8)[1]) == 19109                    # N = 8: one step is the whole day
